@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- SpMV throughput of the B200 hot path on BASELINE.json's metric and config.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; N>1 under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (N=1): BASELINE.json configs[1] -- googleplus-sized graph (107,614 x 107,614, ~13.7 M
+non-zeros; the dataset itself is a download the reference does not ship, so an R-MAT stand-in of
+the same size is generated, seed 0xC0FFEE02), fixed-point path (ap_ufixed<32,8>), one B200.
+A STEP is one batch of `--batch` SpMVs (default 128) over the resident matrix -- the reference's
+benchmark loop (sw/benchmark.cpp:315-343) with 128 instead of 50 back-to-back runs -- so that a
+step lasts milliseconds and GPU clocks can be sampled while it runs. Successive SpMVs rotate over
+enough HBM copies of the matrix that none is still in the 126 MB L2 when it is read again.
+
+Metric (sw/benchmark.cpp:311-346): GOPS = 2*nnz / t ; GBPS = 8*nnz bytes / 2^30 / t.
+`value` = device-timed (CUDA events on the launching stream, inputs resident in HBM);
+`e2e`   = the same metric through the reference-facing C ABI with HOST buffers: every SpMV uploads x
+          from pinned host memory and downloads y (matrix resident, as in the reference).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 0xC0FFEE02
+N_NODES, NNZ_TARGET = 107614, 13_670_000
+L2_BYTES = 126 * 1024 * 1024
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload(rank):
+    """C2 stand-in shard for `rank` (rank 0 == the single-GPU workload)."""
+    from hisparse_b200 import matgen
+    rows, cols, indptr, indices, data = matgen.rmat_csr(N_NODES, NNZ_TARGET, SEED + rank)
+    data = (data * np.float32(0.05)).astype(np.float32)      # keeps most row sums below saturation
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)  # util_round_csr_matrix_dim
+    x = np.zeros(c2, np.float32)
+    x[:cols] = np.random.default_rng(SEED).random(cols, dtype=np.float32)
+    return r2, c2, ip2, indices, data, x
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t0 = self.t1 = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._pump, daemon=True).start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        inside = [r for t, r in self.rows if self.t0 <= t <= self.t1]
+        scope = "timed region"
+        if not inside:
+            inside, scope = [r for _, r in self.rows], "whole run (timed region shorter than the sampling period)"
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in inside:
+            f = [s.strip() for s in r.split(",")]
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path: compute_ref (sw/host.cpp:33-48),
+    compiled unmodified into oracle/_ref; falls back to the oracle's C restatement."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import hsoracle
+    r2, c2, ip2, indices, data, x = workload(0)
+    nnz = int(ip2[-1])
+    if hsoracle.ref_available("fixed"):
+        ref, kind = hsoracle.Ref("fixed"), "reference"
+        one = lambda n: ref.time_compute_ref(r2, c2, ip2, indices, data, x, n)
+    else:
+        port, kind = hsoracle.Port(), "port"
+        one = lambda n: port.time_spmv_f32(ip2, indices, data, x, n)
+    per_step = 4                                   # a step = 4 CPU SpMVs over the same matrix (bounded sample)
+    for _ in range(args.warmup):
+        one(1)
+    t = 0.0
+    for _ in range(args.steps):
+        t += one(per_step) * per_step
+    sec_per_spmv = t / (args.steps * per_step)
+    gops = 2.0 * nnz / sec_per_spmv / 1e9
+    cores = 1
+    out = {"impl": "reference", "metric": "SpMV GOPS (2*nnz/t, sw/benchmark.cpp:312-346)", "value": gops,
+           "unit": "GOPS", "gbps": 8.0 * nnz / 2 ** 30 / sec_per_spmv, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "C2 googleplus-sized R-MAT 107614^2, nnz=%d (fp32 compute_ref, single host thread, "
+                                  "as the reference runs it)" % nnz, "spmv_per_step": per_step},
+           "cpu_baseline": {"value": gops, "unit": "GOPS", "cores": cores, "kind": kind,
+                            "sample": "%d x %d full SpMVs of the C2 matrix" % (args.steps, per_step)},
+           "e2e": {"value": gops, "unit": "GOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def cpu_baseline(r2, c2, ip2, indices, data, x, nnz):
+    from oracle import hsoracle
+    if hsoracle.ref_available("fixed"):
+        ref, kind = hsoracle.Ref("fixed"), "reference"
+        fn = lambda n: ref.time_compute_ref(r2, c2, ip2, indices, data, x, n)
+    else:
+        hsoracle.build()
+        port, kind = hsoracle.Port(), "port"
+        fn = lambda n: port.time_spmv_f32(ip2, indices, data, x, n)
+    t1 = fn(2)
+    runs = int(max(10, min(2000, 10.0 / max(t1, 1e-6))))       # about 10 s of CPU work
+    sec = fn(runs)
+    return {"value": 2.0 * nnz / sec / 1e9, "unit": "GOPS", "gbps": 8.0 * nnz / 2 ** 30 / sec, "cores": 1,
+            "kind": kind, "host_cores_available": os.cpu_count(),
+            "sample": "%d full fp32 SpMVs of the C2 matrix by compute_ref (sw/host.cpp:33-48), 1 thread, mean" % runs}
+
+
+class _DevArray:
+    """expose a raw device pointer to torch through __cuda_array_interface__"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<u4", "data": (ptr, False), "version": 2}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=128, help="SpMVs per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from hisparse_b200 import capi
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    r2, c2, ip2, indices, data, x = workload(rank)
+    nnz = int(ip2[-1])
+    from oracle import hsoracle        # checker only: quantisation of the synthetic inputs + spot check
+    port = hsoracle.Port()
+    words, xw = port.quantize(data), port.quantize(x)
+
+    ctx = capi.Context(local, capi.IMPL_FIXED)
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+    st = ctx.stats()
+    replicas = max(2, int(np.ceil(2.5 * L2_BYTES / max(st["format_bytes"], 1))))
+    ctx.set_replicas(replicas)
+    if world > 1:
+        # every rank needs the same x: NCCL broadcast from rank 0 straight into the engine's x buffer
+        import torch
+        ctx.upload_vector(xw if rank == 0 else np.zeros_like(xw))
+        ctx.sync()
+        xt = torch.as_tensor(_DevArray(ctx.device_x(), c2), device="cuda:%d" % local)
+        dist.broadcast(xt.view(torch.int32), 0)
+        torch.cuda.synchronize()
+    else:
+        ctx.upload_vector(xw)
+    # parity spot check of this very configuration (bit-exact)
+    ctx.spmv()
+    y = ctx.download_result()
+    if not np.array_equal(y, port.spmv_q824(ip2, indices, words, xw)):
+        raise SystemExit("bench: GPU result differs from the oracle -- refusing to report a number")
+
+    B = args.batch
+    launches0 = ctx.stats()["kernel_launches"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.time_spmv(args.warmup * B, 1, kernel=False)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    barrier()
+    launches1 = ctx.stats()["kernel_launches"]
+    sampler.t0 = time.perf_counter()
+    step_ms, _ = ctx.time_spmv(0, args.steps * B, kernel=False)       # CUDA events around K*B SpMVs
+    barrier()
+    sampler.t1 = time.perf_counter()
+    launches2 = ctx.stats()["kernel_launches"]
+    total_ms = step_ms * args.steps * B
+    _, kernel_ms = ctx.time_spmv(0, min(args.steps * B, 512), kernel=True)   # per-launch event pairs
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms, float(nnz)], dtype=torch.float64, device="cuda:%d" % local)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_ms, nnz_all = float(tmax[0]), float(t[1])
+    else:
+        nnz_all = float(nnz)
+    sampler.stop()
+
+    # end to end through the C ABI with host buffers (pinned): upload x, SpMV, download y, per SpMV
+    px, py = capi.PinnedArray(c2), capi.PinnedArray(r2)
+    px.array[:] = xw
+    n_e2e = max(64, min(args.steps * B, 1024))
+    for _ in range(16):
+        ctx.upload_vector(px.array); ctx.spmv(); ctx.download_result(py.array)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        ctx.upload_vector(px.array); ctx.spmv(); ctx.download_result(py.array)
+    ctx.sync()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda:%d" % local)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    assert np.array_equal(py.array, y)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        sec_per_spmv = total_ms / 1e3 / (args.steps * B)
+        gops = 2.0 * nnz_all / sec_per_spmv / 1e9
+        alg = st["algorithmic_bytes"]
+        achieved = alg / (kernel_ms / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        out = {
+            "metric": "SpMV GOPS (2*nnz/t, sw/benchmark.cpp:312-346)", "value": gops, "unit": "GOPS",
+            "gbps": 8.0 * nnz_all / 2 ** 30 / sec_per_spmv,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "ms_per_spmv": 1e3 * sec_per_spmv, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 Q8.24 (ap_ufixed<32,8,AP_RND,AP_SAT>), 64-bit accumulate", "data": "synthetic",
+            "config": {"workload": "C2: googleplus-sized R-MAT 107614^2 (a,b,c=.57,.19,.19), nnz=%d per GPU, fixed-point, "
+                                   "bit-exact vs oracle checked in this run" % nnz,
+                       "spmv_per_step": B, "l2_policy": "inputs larger than L2: %d HBM replicas of the matrix "
+                       "(%.0f MB each) used round-robin" % (replicas, st["format_bytes"] / 1e6),
+                       "sharding": "row-block shard per GPU, x replicated (one NCCL broadcast before timing), "
+                                   "no data-path collective" if world > 1 else "single GPU",
+                       "tile_cols": st["tile_cols"], "col_tiles": st["n_col_tiles"], "grid": st["grid"]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "spmv_tiles_kernel<FixedArith>",
+                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg,
+                         "format_bytes_per_launch": st["format_bytes"],
+                         "note": "achieved uses ALGORITHMIC bytes 8*nnz+4*(rows+1)+4*rows+4*cols; the kernel streams "
+                                 "a 6 B/nnz compressed format, so >1.0 would mean compression, not magic"},
+            "e2e": {"value": 2.0 * nnz_all / e2e_s / 1e9, "unit": "GOPS", "h2d_bytes_per_step": B * c2 * 4,
+                    "d2h_bytes_per_step": B * r2 * 4, "ms_per_spmv": 1e3 * e2e_s,
+                    "what": "per SpMV: hsb_upload_vector(pinned x) + hsb_spmv + hsb_download_result(pinned y); "
+                            "matrix resident as in sw/benchmark.cpp"},
+            "gpu_launches": int(launches2 - launches1),
+            "gpu_launches_per_spmv": (launches2 - launches1) / float(args.steps * B),
+            "clocks": sampler.summary(),
+            "preprocess_s": st["preprocess_seconds"],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(r2, c2, ip2, indices, data, x, nnz)
+        print(json.dumps(out))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

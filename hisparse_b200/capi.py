@@ -1,0 +1,289 @@
+"""ctypes binding of the C ABI declared in include/hisparse_b200.h.
+
+This is glue for tests and bench.py (the reference's host side is C++; the C++ host mirror lives
+in hisparse_b200/host/). There is NO fallback: if libhisparse_b200.so is missing or the CUDA
+device cannot be used, the calls raise.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "libhisparse_b200.so")
+HEADER = os.path.join(ROOT, "include", "hisparse_b200.h")
+
+IMPL_FIXED, IMPL_FLOAT_POB, IMPL_FLOAT_STALL = 0, 1, 2
+IMPL_BY_NAME = {"fixed": 0, "float_pob": 1, "float_stall": 2}
+NUM_HBM_CHANNELS, PACK_SIZE = 16, 8
+
+
+class HsbError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("pack_size", "num_hbm_channels", "interleave_factor",
+                                          "logical_ob_size", "logical_vb_size")]
+
+
+class Stats(C.Structure):
+    _fields_ = [("nnz", C.c_uint64), ("rows", C.c_uint32), ("cols", C.c_uint32), ("n_row_parts", C.c_uint32),
+                ("n_col_tiles", C.c_uint32), ("tile_cols", C.c_uint32), ("n_chunks", C.c_uint64),
+                ("n_segments", C.c_uint64), ("format_bytes", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("sm_count", C.c_uint32), ("grid", C.c_uint32),
+                ("replicas", C.c_uint32), ("preprocess_seconds", C.c_double)]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def build(force=False):
+    """Compile hisparse_b200/libhisparse_b200.so for sm_100a with nvcc (in-tree)."""
+    args = ["make", "-s", "-C", os.path.join(HERE, "csrc")]
+    if force:
+        args.insert(1, "-B")
+    subprocess.run(args, check=True, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def declared_symbols():
+    """Every function name include/hisparse_b200.h declares."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hsb_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HsbError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u32, sz = C.c_void_p, C.c_uint32, C.c_size_t
+    L.hsb_version.restype = C.c_char_p
+    L.hsb_last_error.restype = C.c_char_p
+    L.hsb_get_config.argtypes = [C.c_int, C.POINTER(Config)]
+    L.hsb_create.argtypes = [C.c_int, C.c_int]
+    L.hsb_create.restype = vp
+    L.hsb_destroy.argtypes = [vp]
+    L.hsb_destroy.restype = None
+    L.hsb_host_alloc.argtypes = [sz]
+    L.hsb_host_alloc.restype = vp
+    L.hsb_host_free.argtypes = [vp]
+    L.hsb_host_free.restype = None
+    L.hsb_upload_matrix_cpsr.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.c_uint, C.c_uint, C.c_uint, C.c_uint]
+    L.hsb_upload_matrix_csr.argtypes = [vp, u32, u32, vp, vp, vp, u32]
+    L.hsb_upload_vector.argtypes = [vp, vp, C.c_uint]
+    L.hsb_spmv_row_partition.argtypes = [vp] + [C.c_uint] * 5
+    L.hsb_spmv.argtypes = [vp]
+    L.hsb_sync.argtypes = [vp]
+    L.hsb_download_result.argtypes = [vp, vp, C.c_uint]
+    L.hsb_top_wrapper.argtypes = [C.c_int, C.POINTER(vp), vp, vp] + [C.c_uint] * 5
+    L.hsb_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.hsb_set_replicas.argtypes = [vp, C.c_int]
+    L.hsb_time_spmv.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    for n in ("hsb_device_x", "hsb_device_y", "hsb_stream"):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = vp
+    L.hsb_format_build.argtypes = [u32, u32, vp, vp, vp, u32, u32]
+    L.hsb_format_build.restype = vp
+    L.hsb_format_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.hsb_format_expand.argtypes = [vp, vp, vp, vp]
+    L.hsb_format_free.argtypes = [vp]
+    L.hsb_format_free.restype = None
+    L.hsb_cpsr_to_csr.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(sz), C.c_uint, C.c_uint, C.c_uint, C.c_uint,
+                                  vp, vp, vp, sz, C.POINTER(sz)]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise HsbError("hisparse_b200 error %d: %s" % (rc, lib().hsb_last_error().decode()))
+
+
+def _words(a):
+    """any 32-bit array (uint32 / float32) -> contiguous uint32 view"""
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.float32:
+        return a.view(np.uint32)
+    if a.dtype != np.uint32:
+        a = a.astype(np.uint32)
+    return a
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def get_config(impl):
+    cfg = Config()
+    _check(lib().hsb_get_config(impl, C.byref(cfg)))
+    return cfg
+
+
+def device_count():
+    return lib().hsb_device_count()
+
+
+def _images_args(images):
+    imgs = [np.ascontiguousarray(im, dtype=np.uint32) for im in images]
+    arr = (C.c_void_p * 16)(*[im.ctypes.data for im in imgs])
+    lens = (C.c_size_t * 16)(*[im.size // 16 for im in imgs])
+    return imgs, arr, lens
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory from hsb_host_alloc."""
+
+    def __init__(self, n_words, dtype=np.uint32):
+        self._p = lib().hsb_host_alloc(n_words * 4)
+        if not self._p:
+            raise HsbError("hsb_host_alloc failed")
+        buf = (C.c_uint32 * n_words).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype, count=n_words)
+
+    def __del__(self):
+        try:
+            self.array = None
+            lib().hsb_host_free(self._p)
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU, one implementation (fixed / float_pob / float_stall): mirrors the reference's
+    cl_runtime struct (sw/host.cpp:120-128)."""
+
+    def __init__(self, device=0, impl=IMPL_FIXED):
+        if isinstance(impl, str):
+            impl = IMPL_BY_NAME[impl]
+        self.impl = impl
+        self.h = lib().hsb_create(device, impl)
+        if not self.h:
+            raise HsbError("hsb_create failed: " + lib().hsb_last_error().decode())
+        self.rows = self.cols = 0
+
+    def close(self):
+        if self.h:
+            lib().hsb_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def upload_matrix_csr(self, rows, cols, indptr, indices, vals, rows_per_partition=0):
+        indptr, indices, vals = _words(indptr), _words(indices), _words(vals)
+        assert indptr.size == rows + 1
+        _check(lib().hsb_upload_matrix_csr(self.h, rows, cols, _ptr(indptr), _ptr(indices), _ptr(vals),
+                                           rows_per_partition))
+        self.rows, self.cols = rows, cols
+
+    def upload_matrix_cpsr(self, images, n_row_parts, n_col_parts, rows, cols):
+        imgs, arr, lens = _images_args(images)
+        _check(lib().hsb_upload_matrix_cpsr(self.h, arr, lens, n_row_parts, n_col_parts, rows, cols))
+        self.rows, self.cols = rows, cols
+
+    def upload_vector(self, x):
+        x = _words(x)
+        _check(lib().hsb_upload_vector(self.h, _ptr(x), x.size))
+
+    def spmv_row_partition(self, row_part_id, part_len, ncp, nparts, num_cols):
+        _check(lib().hsb_spmv_row_partition(self.h, row_part_id, part_len, ncp, nparts, num_cols))
+
+    def spmv(self):
+        _check(lib().hsb_spmv(self.h))
+
+    def sync(self):
+        _check(lib().hsb_sync(self.h))
+
+    def download_result(self, out=None, dtype=np.uint32):
+        if out is None:
+            out = np.empty(self.rows, dtype)
+        _check(lib().hsb_download_result(self.h, _ptr(out), out.size))
+        return out
+
+    def stats(self):
+        s = Stats()
+        _check(lib().hsb_get_stats(self.h, C.byref(s)))
+        return s.asdict()
+
+    def set_replicas(self, n):
+        _check(lib().hsb_set_replicas(self.h, n))
+
+    def time_spmv(self, warmup, steps, kernel=True):
+        a, b = C.c_float(), C.c_float()
+        _check(lib().hsb_time_spmv(self.h, warmup, steps, C.byref(a), C.byref(b) if kernel else None))
+        return a.value, (b.value if kernel else None)
+
+    def device_x(self):
+        return lib().hsb_device_x(self.h)
+
+    def device_y(self):
+        return lib().hsb_device_y(self.h)
+
+    def stream(self):
+        return lib().hsb_stream(self.h)
+
+
+def top_wrapper(impl, images, x, y, row_part_id, part_len, ncp, nparts, num_cols):
+    """spmv_csim/csim.cpp:22-46 with host buffers; y (uint32 words) is written in place."""
+    if isinstance(impl, str):
+        impl = IMPL_BY_NAME[impl]
+    imgs, arr, _ = _images_args(images)
+    x = _words(x)
+    assert y.dtype == np.uint32 and y.flags.c_contiguous
+    _check(lib().hsb_top_wrapper(impl, arr, _ptr(x), _ptr(y), row_part_id, part_len, ncp, nparts, num_cols))
+
+
+class Format:
+    """Host-side view of the tile-stream format (no GPU)."""
+
+    def __init__(self, rows, cols, indptr, indices, vals, rows_per_partition=0, tile_cols=0):
+        indptr, indices, vals = _words(indptr), _words(indices), _words(vals)
+        self.rows, self.nnz = rows, int(indptr[-1]) if indptr.size else 0
+        self.h = lib().hsb_format_build(rows, cols, _ptr(indptr), _ptr(indices), _ptr(vals), rows_per_partition,
+                                        tile_cols)
+        if not self.h:
+            raise HsbError("hsb_format_build rejected the matrix")
+
+    def stats(self):
+        s = Stats()
+        _check(lib().hsb_format_stats(self.h, C.byref(s)))
+        return s.asdict()
+
+    def expand(self):
+        indptr = np.zeros(self.rows + 1, np.uint32)
+        indices = np.zeros(max(self.nnz, 1), np.uint32)
+        vals = np.zeros(max(self.nnz, 1), np.uint32)
+        _check(lib().hsb_format_expand(self.h, _ptr(indptr), _ptr(indices), _ptr(vals)))
+        return indptr, indices[:self.nnz], vals[:self.nnz]
+
+    def __del__(self):
+        try:
+            lib().hsb_format_free(self.h)
+        except Exception:
+            pass
+
+
+def cpsr_to_csr(impl, images, n_row_parts, n_col_parts, rows, cols):
+    if isinstance(impl, str):
+        impl = IMPL_BY_NAME[impl]
+    imgs, arr, lens = _images_args(images)
+    nnz = C.c_size_t()
+    _check(lib().hsb_cpsr_to_csr(impl, arr, lens, n_row_parts, n_col_parts, rows, cols, None, None, None, 0,
+                                 C.byref(nnz)))
+    indptr = np.zeros(rows + 1, np.uint32)
+    indices = np.zeros(max(nnz.value, 1), np.uint32)
+    vals = np.zeros(max(nnz.value, 1), np.uint32)
+    _check(lib().hsb_cpsr_to_csr(impl, arr, lens, n_row_parts, n_col_parts, rows, cols, _ptr(indptr), _ptr(indices),
+                                 _ptr(vals), indices.size, C.byref(nnz)))
+    return indptr, indices[:nnz.value], vals[:nnz.value]

@@ -1,0 +1,415 @@
+// C ABI (include/hisparse_b200.h) over the CUDA runtime: the thin shim that replaces the
+// reference's OpenCL host calls (sw/host.cpp:263-371; xrt/includes/xcl2).
+#include "../../include/hisparse_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cpsr_decode.h"
+#include "spmv_kernels.cuh"
+#include "tile_format.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int set_err(int code, const std::string &m) { g_err = m; return code; }
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            char b__[512];                                                                          \
+            std::snprintf(b__, sizeof b__, "CUDA error at %s:%d: %s (%s)", __FILE__, __LINE__,      \
+                          cudaGetErrorString(e__), #expr);                                          \
+            return set_err(HSB_ECUDA, b__);                                                         \
+        }                                                                                           \
+    } while (0)
+
+struct DeviceMatrix {
+    uint32_t *vals = nullptr;
+    uint16_t *cidx = nullptr;
+    hsb::ChunkDesc *chunks = nullptr;
+    hsb::TileDesc *tiles = nullptr;
+    uint32_t *seg_row = nullptr;
+    void release() {
+        cudaFree(vals); cudaFree(cidx); cudaFree(chunks); cudaFree(tiles); cudaFree(seg_row);
+        vals = nullptr; cidx = nullptr; chunks = nullptr; tiles = nullptr; seg_row = nullptr;
+    }
+};
+
+}  // namespace
+
+struct hsb_ctx {
+    int device = 0, impl = 0, arith = 0;
+    hsb::ImplConfig cfg{};
+    cudaStream_t stream = nullptr;
+    int sm_count = 0, grid = 0;
+    // resident matrix
+    bool have_matrix = false;
+    uint32_t rows = 0, cols = 0, x_words = 0;
+    uint64_t nnz = 0;
+    uint32_t rows_per_part = 0, n_row_parts = 0, n_col_tiles = 0, tile_cols = 0;
+    uint64_t n_chunks = 0, n_segments = 0, format_bytes = 0;
+    std::vector<uint32_t> part_chunk_begin;
+    std::vector<DeviceMatrix> mats;       // [0] + replicas
+    size_t sz_vals = 0, sz_cidx = 0, sz_chunks = 0, sz_tiles = 0, sz_seg = 0;
+    unsigned next_replica = 0;
+    // vectors
+    uint32_t *d_x = nullptr;              // x_words words (padded to whole tiles, zero filled)
+    uint32_t *d_y = nullptr;              // rows words
+    unsigned long long *d_acc = nullptr;  // fixed: 64-bit row accumulators
+    uint64_t launches = 0;
+    double preprocess_s = 0;
+};
+
+namespace {
+
+void free_matrix(hsb_ctx *c) {
+    for (auto &m : c->mats) m.release();
+    c->mats.clear();
+    cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_acc);
+    c->d_x = nullptr; c->d_y = nullptr; c->d_acc = nullptr;
+    c->have_matrix = false;
+}
+
+int upload_tiled(hsb_ctx *c, const hsb::TiledMatrix &M) {
+    CUDA_TRY(cudaSetDevice(c->device));
+    free_matrix(c);
+    c->rows = M.rows; c->cols = M.cols; c->nnz = M.nnz;
+    c->rows_per_part = M.rows_per_part; c->n_row_parts = M.n_row_parts;
+    c->n_col_tiles = M.n_col_tiles; c->tile_cols = M.tile_cols;
+    c->n_chunks = M.n_chunks(); c->n_segments = M.seg_row.size(); c->format_bytes = M.format_bytes();
+    c->part_chunk_begin = M.part_chunk_begin;
+    c->sz_vals = M.vals.size() * 4; c->sz_cidx = M.cidx.size() * 2;
+    c->sz_chunks = M.chunks.size() * sizeof(hsb::ChunkDesc); c->sz_tiles = M.tiles.size() * sizeof(hsb::TileDesc);
+    c->sz_seg = M.seg_row.size() * 4;
+    DeviceMatrix d;
+    CUDA_TRY(cudaMalloc(&d.vals, c->sz_vals + 16));
+    CUDA_TRY(cudaMalloc(&d.cidx, c->sz_cidx + 16));
+    CUDA_TRY(cudaMalloc(&d.chunks, c->sz_chunks + 16));
+    CUDA_TRY(cudaMalloc(&d.tiles, c->sz_tiles + 16));
+    CUDA_TRY(cudaMalloc(&d.seg_row, c->sz_seg + 16));
+    CUDA_TRY(cudaMemcpyAsync(d.vals, M.vals.data(), c->sz_vals, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.cidx, M.cidx.data(), c->sz_cidx, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.chunks, M.chunks.data(), c->sz_chunks, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.tiles, M.tiles.data(), c->sz_tiles, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.seg_row, M.seg_row.data(), c->sz_seg, cudaMemcpyHostToDevice, c->stream));
+    c->mats.push_back(d);
+    // x is padded to whole tiles so that every bulk copy of a tile stays inside the buffer
+    c->x_words = M.n_col_tiles * M.tile_cols;
+    CUDA_TRY(cudaMalloc(&c->d_x, (size_t)c->x_words * 4 + 16));
+    CUDA_TRY(cudaMemsetAsync(c->d_x, 0, (size_t)c->x_words * 4, c->stream));
+    CUDA_TRY(cudaMalloc(&c->d_y, (size_t)std::max(c->rows, 1u) * 4));
+    CUDA_TRY(cudaMemsetAsync(c->d_y, 0, (size_t)std::max(c->rows, 1u) * 4, c->stream));
+    if (c->arith == hsb::kArithFixed) CUDA_TRY(cudaMalloc(&c->d_acc, (size_t)std::max(c->rows, 1u) * 8));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count, c->n_chunks));
+    c->next_replica = 0;
+    c->have_matrix = true;
+    return HSB_OK;
+}
+
+// one SpMV over chunk range [cb, ce) / rows [rb, re); optional event pair around the tile kernel
+int run_range(hsb_ctx *c, uint32_t cb, uint32_t ce, uint32_t rb, uint32_t re, cudaEvent_t k0, cudaEvent_t k1) {
+    const DeviceMatrix &m = c->mats[c->next_replica % c->mats.size()];
+    c->next_replica++;
+    void *acc = c->arith == hsb::kArithFixed ? (void *)c->d_acc : (void *)c->d_y;
+    size_t esz = c->arith == hsb::kArithFixed ? 8 : 4;
+    if (re > rb) CUDA_TRY(cudaMemsetAsync((char *)acc + (size_t)rb * esz, 0, (size_t)(re - rb) * esz, c->stream));
+    hsb::SpmvParams p;
+    p.vals = m.vals; p.cidx = m.cidx; p.chunks = m.chunks; p.tiles = m.tiles; p.seg_row = m.seg_row;
+    p.x = c->d_x; p.acc = acc; p.chunk_begin = cb; p.chunk_end = ce;
+    if (k0) CUDA_TRY(cudaEventRecord(k0, c->stream));
+    if (ce > cb) {
+        int grid = (int)std::min<uint64_t>((uint64_t)c->grid, ce - cb);
+        hsb::launch_spmv_tiles(c->arith, p, grid, c->stream);
+        c->launches++;
+    }
+    if (k1) CUDA_TRY(cudaEventRecord(k1, c->stream));
+    if (c->arith == hsb::kArithFixed && re > rb) {
+        hsb::launch_finalize_fixed(c->d_acc, c->d_y, rb, re, c->stream);
+        c->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return HSB_OK;
+}
+
+int run_all(hsb_ctx *c, cudaEvent_t k0, cudaEvent_t k1) {
+    return run_range(c, 0, (uint32_t)c->n_chunks, 0, c->rows, k0, k1);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *hsb_version(void) { return "hisparse_b200 0.1 (sm_100a)"; }
+const char *hsb_last_error(void) { return g_err.c_str(); }
+
+int hsb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int hsb_get_config(int impl, hsb_config *out) {
+    hsb::ImplConfig cfg;
+    if (!out || !hsb::impl_config(impl, &cfg)) return set_err(HSB_EINVAL, "unknown impl");
+    out->pack_size = HSB_PACK_SIZE; out->num_hbm_channels = HSB_NUM_HBM_CHANNELS;
+    out->interleave_factor = cfg.interleave; out->logical_ob_size = cfg.ob_size; out->logical_vb_size = cfg.vb_size;
+    return HSB_OK;
+}
+
+hsb_ctx *hsb_create(int device, int impl) {
+    hsb::ImplConfig cfg;
+    if (!hsb::impl_config(impl, &cfg)) { set_err(HSB_EINVAL, "unknown impl"); return nullptr; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || device < 0 || device >= n) {
+        set_err(HSB_ECUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    hsb_ctx *c = new hsb_ctx;
+    c->device = device; c->impl = impl; c->cfg = cfg;
+    c->arith = impl == HSB_IMPL_FIXED ? hsb::kArithFixed : hsb::kArithFloat;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_err(HSB_ECUDA, std::string("device setup failed: ") + cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return nullptr;
+    }
+    if (prop.major != 10) {
+        set_err(HSB_ECUDA, "this build contains sm_100a code only; device is not compute capability 10.x");
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return nullptr;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    e = hsb::configure_kernels();
+    if (e != cudaSuccess) {
+        set_err(HSB_ECUDA, std::string("kernel configuration failed: ") + cudaGetErrorString(e));
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+
+void hsb_destroy(hsb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_matrix(c);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void *hsb_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void hsb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int hsb_upload_matrix_csr(hsb_ctx *c, uint32_t rows, uint32_t cols, const uint32_t *indptr,
+                          const uint32_t *indices, const void *vals, uint32_t rows_per_partition) {
+    if (!c || !indptr || (rows && indptr[rows] && (!indices || !vals))) return set_err(HSB_EINVAL, "null argument");
+    auto t0 = std::chrono::steady_clock::now();
+    hsb::TiledMatrix M;
+    std::string err;
+    if (!hsb::build_tiled(rows, cols, indptr, indices, (const uint32_t *)vals, rows_per_partition,
+                          hsb::choose_tile_cols(cols), 0, &M, &err))
+        return set_err(HSB_EINVAL, "malformed CSR: " + err);
+    c->preprocess_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return upload_tiled(c, M);
+}
+
+int hsb_upload_matrix_cpsr(hsb_ctx *c, const void *const ch[HSB_NUM_HBM_CHANNELS],
+                           const size_t ch_packets[HSB_NUM_HBM_CHANNELS], unsigned num_row_partitions,
+                           unsigned num_col_partitions, unsigned num_rows, unsigned num_cols) {
+    if (!c || !ch || !ch_packets) return set_err(HSB_EINVAL, "null argument");
+    if (num_rows % 128u || num_cols % 8u) return set_err(HSB_EINVAL, "rows must divide 128 and cols 8 (util_round_csr_matrix_dim)");
+    if (num_row_partitions != (num_rows + c->cfg.ob_size - 1) / c->cfg.ob_size ||
+        num_col_partitions != (num_cols + c->cfg.vb_size - 1) / c->cfg.vb_size)
+        return set_err(HSB_EINVAL, "partition counts do not match the implementation's buffer sizes");
+    auto t0 = std::chrono::steady_clock::now();
+    const uint32_t *imgs[16];
+    for (int i = 0; i < 16; i++) imgs[i] = (const uint32_t *)ch[i];
+    std::vector<uint32_t> rows_in(num_row_partitions);
+    for (unsigned j = 0; j < num_row_partitions; j++)
+        rows_in[j] = std::min<uint64_t>(c->cfg.ob_size, (uint64_t)num_rows - (uint64_t)j * c->cfg.ob_size);
+    hsb::HostCsr csr;
+    std::string err;
+    if (!hsb::cpsr_decode(c->cfg, imgs, ch_packets, num_row_partitions, num_col_partitions, 0, num_row_partitions,
+                          rows_in.data(), num_cols, &csr, &err))
+        return set_err(HSB_EINVAL, "malformed CPSR image: " + err);
+    hsb::TiledMatrix M;
+    if (!hsb::build_tiled(csr.rows, csr.cols, csr.indptr.data(), csr.indices.data(), csr.vals.data(),
+                          c->cfg.ob_size, hsb::choose_tile_cols(csr.cols), 0, &M, &err))
+        return set_err(HSB_EINVAL, "malformed CPSR image: " + err);
+    c->preprocess_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return upload_tiled(c, M);
+}
+
+int hsb_upload_vector(hsb_ctx *c, const void *x_packed, unsigned num_cols) {
+    if (!c || !x_packed) return set_err(HSB_EINVAL, "null argument");
+    if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
+    if (num_cols > c->x_words || num_cols < c->cols) return set_err(HSB_EINVAL, "num_cols does not match the matrix");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(c->d_x, x_packed, (size_t)num_cols * 4, cudaMemcpyHostToDevice, c->stream));
+    return HSB_OK;
+}
+
+int hsb_spmv_row_partition(hsb_ctx *c, unsigned row_part_id, unsigned part_len, unsigned num_col_partitions,
+                           unsigned num_partitions, unsigned num_cols) {
+    if (!c) return set_err(HSB_EINVAL, "null context");
+    if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
+    if (row_part_id >= c->n_row_parts) return set_err(HSB_EINVAL, "row_part_id out of range");
+    uint32_t rb = row_part_id * c->rows_per_part;
+    uint32_t re = (uint32_t)std::min<uint64_t>(c->rows, (uint64_t)rb + c->rows_per_part);
+    if ((uint64_t)part_len * HSB_NUM_HBM_CHANNELS != re - rb)
+        return set_err(HSB_EINVAL, "part_len does not match the rows of this partition");
+    if (num_cols < c->cols || num_cols > c->x_words || (num_col_partitions && num_partitions % num_col_partitions))
+        return set_err(HSB_EINVAL, "num_cols / partition counts do not match the matrix");
+    CUDA_TRY(cudaSetDevice(c->device));
+    return run_range(c, c->part_chunk_begin[row_part_id], c->part_chunk_begin[row_part_id + 1], rb, re, nullptr, nullptr);
+}
+
+int hsb_spmv(hsb_ctx *c) {
+    if (!c) return set_err(HSB_EINVAL, "null context");
+    if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    return run_all(c, nullptr, nullptr);
+}
+
+int hsb_sync(hsb_ctx *c) {
+    if (!c) return set_err(HSB_EINVAL, "null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HSB_OK;
+}
+
+int hsb_download_result(hsb_ctx *c, void *y_packed, unsigned num_rows) {
+    if (!c || !y_packed) return set_err(HSB_EINVAL, "null argument");
+    if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
+    if (num_rows > c->rows) return set_err(HSB_EINVAL, "num_rows exceeds the matrix");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(y_packed, c->d_y, (size_t)num_rows * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HSB_OK;
+}
+
+int hsb_top_wrapper(int impl, const void *const matrix_hbm[HSB_NUM_HBM_CHANNELS], const void *x, void *y,
+                    unsigned row_part_id, unsigned part_len, unsigned num_col_partitions,
+                    unsigned num_partitions, unsigned num_cols) {
+    hsb::ImplConfig cfg;
+    if (!hsb::impl_config(impl, &cfg)) return set_err(HSB_EINVAL, "unknown impl");
+    if (!matrix_hbm || !x || !y || !num_col_partitions || num_partitions % num_col_partitions)
+        return set_err(HSB_EINVAL, "bad argument");
+    const unsigned nrp = num_partitions / num_col_partitions;
+    if (row_part_id >= nrp) return set_err(HSB_EINVAL, "row_part_id out of range");
+    const uint32_t *imgs[16];
+    size_t lens[16];
+    for (int i = 0; i < 16; i++) {
+        imgs[i] = (const uint32_t *)matrix_hbm[i];
+        lens[i] = hsb::cpsr_image_packets(cfg, imgs[i], num_partitions);
+    }
+    uint32_t rows_here = part_len * HSB_NUM_HBM_CHANNELS;
+    hsb::HostCsr csr;
+    std::string err;
+    if (!hsb::cpsr_decode(cfg, imgs, lens, nrp, num_col_partitions, row_part_id, row_part_id + 1, &rows_here,
+                          num_cols, &csr, &err))
+        return set_err(HSB_EINVAL, "malformed CPSR image: " + err);
+    hsb_ctx *c = hsb_create(0, impl);
+    if (!c) return HSB_ECUDA;
+    int rc = hsb_upload_matrix_csr(c, csr.rows, csr.cols, csr.indptr.data(), csr.indices.data(), csr.vals.data(), 0);
+    if (rc == HSB_OK) rc = hsb_upload_vector(c, x, num_cols);
+    if (rc == HSB_OK) rc = hsb_spmv(c);
+    // the result drain writes at row_part_id * LOGICAL_OB_SIZE (spmv_result_drain.cpp:36)
+    if (rc == HSB_OK) rc = hsb_download_result(c, (uint32_t *)y + (size_t)row_part_id * cfg.ob_size, rows_here);
+    std::string keep = g_err;
+    hsb_destroy(c);
+    g_err = keep;
+    return rc;
+}
+
+int hsb_get_stats(hsb_ctx *c, hsb_stats *out) {
+    if (!c || !out) return set_err(HSB_EINVAL, "null argument");
+    std::memset(out, 0, sizeof *out);
+    out->nnz = c->nnz; out->rows = c->rows; out->cols = c->cols;
+    out->n_row_parts = c->n_row_parts; out->n_col_tiles = c->n_col_tiles; out->tile_cols = c->tile_cols;
+    out->n_chunks = c->n_chunks; out->n_segments = c->n_segments; out->format_bytes = c->format_bytes;
+    out->algorithmic_bytes = 8ull * c->nnz + 4ull * ((uint64_t)c->rows + 1) + 4ull * c->rows + 4ull * c->cols;
+    out->kernel_launches = c->launches; out->sm_count = c->sm_count; out->grid = c->grid;
+    out->replicas = (uint32_t)c->mats.size(); out->preprocess_seconds = c->preprocess_s;
+    return HSB_OK;
+}
+
+int hsb_set_replicas(hsb_ctx *c, int n) {
+    if (!c || n < 1) return set_err(HSB_EINVAL, "bad argument");
+    if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    while ((int)c->mats.size() > n) { c->mats.back().release(); c->mats.pop_back(); }
+    while ((int)c->mats.size() < n) {
+        DeviceMatrix d;
+        const DeviceMatrix &s = c->mats[0];
+        CUDA_TRY(cudaMalloc(&d.vals, c->sz_vals + 16));
+        CUDA_TRY(cudaMalloc(&d.cidx, c->sz_cidx + 16));
+        CUDA_TRY(cudaMalloc(&d.chunks, c->sz_chunks + 16));
+        CUDA_TRY(cudaMalloc(&d.tiles, c->sz_tiles + 16));
+        CUDA_TRY(cudaMalloc(&d.seg_row, c->sz_seg + 16));
+        CUDA_TRY(cudaMemcpyAsync(d.vals, s.vals, c->sz_vals, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(d.cidx, s.cidx, c->sz_cidx, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(d.chunks, s.chunks, c->sz_chunks, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(d.tiles, s.tiles, c->sz_tiles, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(d.seg_row, s.seg_row, c->sz_seg, cudaMemcpyDeviceToDevice, c->stream));
+        c->mats.push_back(d);
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HSB_OK;
+}
+
+int hsb_time_spmv(hsb_ctx *c, int warmup, int steps, float *step_ms, float *kernel_ms) {
+    if (!c || steps < 1 || warmup < 0) return set_err(HSB_EINVAL, "bad argument");
+    if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    for (int i = 0; i < warmup; i++) { int rc = run_all(c, nullptr, nullptr); if (rc) return rc; }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < steps; i++) { int rc = run_all(c, nullptr, nullptr); if (rc) return rc; }
+    CUDA_TRY(cudaEventRecord(e1, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (step_ms) *step_ms = ms / steps;
+    if (kernel_ms) {
+        std::vector<cudaEvent_t> ev(2 * (size_t)steps);
+        for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+        for (int i = 0; i < steps; i++) { int rc = run_all(c, ev[2 * i], ev[2 * i + 1]); if (rc) return rc; }
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        double tot = 0;
+        for (int i = 0; i < steps; i++) { float t = 0; CUDA_TRY(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1])); tot += t; }
+        for (auto &e : ev) cudaEventDestroy(e);
+        *kernel_ms = (float)(tot / steps);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return HSB_OK;
+}
+
+void *hsb_device_x(hsb_ctx *c) { return c ? c->d_x : nullptr; }
+void *hsb_device_y(hsb_ctx *c) { return c ? c->d_y : nullptr; }
+void *hsb_stream(hsb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+}  // extern "C"

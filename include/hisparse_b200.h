@@ -1,0 +1,160 @@
+/*
+ * hisparse_b200.h -- C ABI of the B200-native SpMV engine that stands in for HiSparse's
+ * FPGA kernel pipeline (spmv_vector_loader -> spmv_sk0/1/2 -> spmv_result_drain).
+ *
+ * The reference has no plugin/FFI registry; its host <-> accelerator boundary is the kernel
+ * argument contract, which exists in two equivalent forms:
+ *   (1) the OpenCL form   sw/host.cpp:263-371   (16 CL_BUFFER_RDONLY channel images + x + y,
+ *       enqueueMigrateMemObjects, setArg, 5 x enqueueTask + finish per row partition) and
+ *   (2) the C-simulation form   spmv_csim/csim.cpp:22-46   `top_wrapper(...)`.
+ * Every entry point below names the reference interface it replaces. Plain pointers and sizes
+ * only; all buffers are HOST buffers unless the name says `device`. All functions returning
+ * `int` return 0 on success and a negative HSB_E* code on failure; hsb_last_error() gives the
+ * message (the reference prints file:line and exits, xrt/includes/xcl2/xcl2.hpp:40-46 -- the C++
+ * wrapper in hisparse_b200/host/ reproduces that behaviour on top of these codes).
+ *
+ * Value words are always 32 bits: raw Q8.24 (ap_ufixed<32,8,AP_RND,AP_SAT>,
+ * spmv/libfpga/common.h:35-38) for HSB_IMPL_FIXED, IEEE fp32 bits for the float variants.
+ */
+#ifndef HISPARSE_B200_H_
+#define HISPARSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSB_NUM_HBM_CHANNELS 16     /* spmv/libfpga/common.h:173-176 : 4 + 6 + 6 clusters */
+#define HSB_PACK_SIZE 8             /* spmv/libfpga/common.h:30 */
+#define HSB_IDX_MARKER 0xFFFFFFFFu  /* spmv/libfpga/common.h:8 */
+
+/* IMPL= of sw/Makefile:2-12 and spmv_csim/Makefile:27-38 */
+enum { HSB_IMPL_FIXED = 0, HSB_IMPL_FLOAT_POB = 1, HSB_IMPL_FLOAT_STALL = 2 };
+
+enum {
+    HSB_OK = 0,
+    HSB_EINVAL = -1,     /* bad argument / malformed matrix or channel image */
+    HSB_ECUDA = -2,      /* CUDA runtime error (message has the CUDA error string) */
+    HSB_ESTATE = -3,     /* call order violated (e.g. spmv before a matrix upload) */
+    HSB_ENOMEM = -4
+};
+
+typedef struct hsb_ctx hsb_ctx;
+
+/* compile-time constants of the selected implementation, as the reference's common.h defines them
+ * (spmv/libfpga/common.h:162-179, spmv-fp/libfpga/common.h:178-199) */
+typedef struct hsb_config {
+    uint32_t pack_size;            /* 8 */
+    uint32_t num_hbm_channels;     /* 16 */
+    uint32_t interleave_factor;    /* 1 (fixed, float_pob) or 8 (float_stall) */
+    uint32_t logical_ob_size;      /* rows per row partition: 1048576 / 131072 / 1048576 */
+    uint32_t logical_vb_size;      /* columns per column partition: 32768 */
+} hsb_config;
+
+typedef struct hsb_stats {
+    uint64_t nnz;                  /* non-zeros of the resident matrix */
+    uint32_t rows, cols;           /* padded dimensions */
+    uint32_t n_row_parts, n_col_tiles, tile_cols;
+    uint64_t n_chunks, n_segments;
+    uint64_t format_bytes;         /* bytes of the tile-stream format in HBM */
+    uint64_t algorithmic_bytes;    /* 8*nnz + 4*(rows+1) + 4*rows + 4*cols   */
+    uint64_t kernel_launches;      /* kernels of this library launched so far on this context */
+    uint32_t sm_count, grid;
+    uint32_t replicas;
+    double preprocess_seconds;     /* host formatting time of the last upload ("Preprocessing" in benchmark.cpp:80-87) */
+} hsb_stats;
+
+const char *hsb_version(void);
+const char *hsb_last_error(void);
+int hsb_device_count(void);
+int hsb_get_config(int impl, hsb_config *out);
+
+/* == cl::Context + cl::CommandQueue + cl::Kernel x5 (sw/host.cpp:556-590). One context per GPU. */
+hsb_ctx *hsb_create(int device, int impl);
+void hsb_destroy(hsb_ctx *ctx);
+
+/* Page-locked host memory: the reference's aligned_allocator (xrt/includes/xcl2/xcl2.hpp:61-76)
+ * gives page-aligned host vectors that the device buffers alias (CL_MEM_USE_HOST_PTR). */
+void *hsb_host_alloc(size_t bytes);
+void hsb_host_free(void *p);
+
+/* == the 16 CL_BUFFER_RDONLY channel buffers + enqueueMigrateMemObjects (sw/host.cpp:263-299).
+ * ch[c] points at ch_packets[c] 64-byte packets laid out exactly as sw/host.cpp:163-231 builds
+ * them (header packets, then data packets, interleaved for float_stall). num_rows / num_cols are
+ * the padded matrix dimensions (the reference passes them through part_len / num_cols later). */
+int hsb_upload_matrix_cpsr(hsb_ctx *ctx, const void *const ch[HSB_NUM_HBM_CHANNELS],
+                           const size_t ch_packets[HSB_NUM_HBM_CHANNELS], unsigned num_row_partitions,
+                           unsigned num_col_partitions, unsigned num_rows, unsigned num_cols);
+
+/* Fast path that skips CPSR: hand over the CSR the reference's formatter would consume
+ * (spmv::io::CSRMatrix<VAL_T>, sw/data_loader.h:19-30) -- vals are 32-bit VAL_T words.
+ * rows_per_partition: row-partition length (LOGICAL_OB_SIZE); 0 = a single partition. */
+int hsb_upload_matrix_csr(hsb_ctx *ctx, uint32_t rows, uint32_t cols, const uint32_t *indptr,
+                          const uint32_t *indices, const void *vals, uint32_t rows_per_partition);
+
+/* == vector_buf on HBM[20] + migrate (sw/host.cpp:282-298). x_packed: num_cols 32-bit words. */
+int hsb_upload_vector(hsb_ctx *ctx, const void *x_packed, unsigned num_cols);
+
+/* == setArg(row_part_id, part_len) + enqueueTask x5 + finish for ONE row partition
+ * (sw/host.cpp:335-357; kernel arguments spmv/spmv_sk0.cpp:13-24, spmv_vector_loader.cpp:95-101,
+ * spmv_result_drain.cpp:11-18). part_len = rows per cluster in this partition (rows / 16). The
+ * call is asynchronous on the context's stream; hsb_sync() is the finish(). */
+int hsb_spmv_row_partition(hsb_ctx *ctx, unsigned row_part_id, unsigned part_len,
+                           unsigned num_col_partitions, unsigned num_partitions, unsigned num_cols);
+
+/* all row partitions back to back (the loop at sw/benchmark.cpp:317-340), asynchronous */
+int hsb_spmv(hsb_ctx *ctx);
+int hsb_sync(hsb_ctx *ctx);
+
+/* == enqueueMigrateMemObjects(result_buf -> host) + finish (sw/host.cpp:370-371).
+ * y_packed: num_rows 32-bit words, natural row order. Synchronises. */
+int hsb_download_result(hsb_ctx *ctx, void *y_packed, unsigned num_rows);
+
+/* == spmv_csim/csim.cpp:22-46 `top_wrapper`: one row partition, host buffers in, host buffer out.
+ * Channel image lengths are recovered from the image headers. Uploads, runs, downloads. */
+int hsb_top_wrapper(int impl, const void *const matrix_hbm[HSB_NUM_HBM_CHANNELS],
+                    const void *packed_dense_vector, void *packed_dense_result, unsigned row_part_id,
+                    unsigned part_len, unsigned num_col_partitions, unsigned num_partitions,
+                    unsigned num_cols);
+
+/* ---- measurement and multi-GPU plumbing (no reference counterpart) ------------------------ */
+int hsb_get_stats(hsb_ctx *ctx, hsb_stats *out);
+/* keep n copies of the matrix in HBM and rotate through them on successive hsb_spmv() calls so
+ * that a timed loop never re-reads a matrix that is still in the 126 MB L2 */
+int hsb_set_replicas(hsb_ctx *ctx, int n);
+/* CUDA-event timing on the context's stream: `steps` full SpMVs after `warmup` untimed ones.
+ * step_ms = (stop - start) / steps over the whole loop; kernel_ms = mean duration of the main
+ * tile kernel alone, from per-launch event pairs in a second loop of the same length. */
+int hsb_time_spmv(hsb_ctx *ctx, int warmup, int steps, float *step_ms, float *kernel_ms);
+/* raw device pointers / stream for callers that move x or y with NCCL (torch.distributed) */
+void *hsb_device_x(hsb_ctx *ctx);
+void *hsb_device_y(hsb_ctx *ctx);
+void *hsb_stream(hsb_ctx *ctx);
+
+/* ---- host-side format inspection (no GPU needed; used by the CPU test-suite) --------------- */
+typedef struct hsb_format hsb_format;
+/* CSR -> tile-stream format on the host, exactly as hsb_upload_matrix_csr builds it.
+ * tile_cols == 0 picks the width automatically. NULL on malformed input. */
+hsb_format *hsb_format_build(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uint32_t *indices,
+                             const void *vals, uint32_t rows_per_partition, uint32_t tile_cols);
+int hsb_format_stats(const hsb_format *f, hsb_stats *out);
+/* Walk the chunk stream the way the kernel addresses it (value slots, end-of-segment flags,
+ * seg_row, chunk descriptors) and rebuild the CSR. indices/vals hold nnz words each. Returns
+ * HSB_EINVAL if the stream is internally inconsistent. Entries of a row come back grouped by
+ * column tile, CSR order inside a tile. */
+int hsb_format_expand(const hsb_format *f, uint32_t *indptr, uint32_t *indices, uint32_t *vals);
+void hsb_format_free(hsb_format *f);
+/* Decode reference channel images back to CSR (what hsb_upload_matrix_cpsr does first).
+ * indptr: num_rows + 1 words; indices / vals: capacity words each; *nnz receives the count
+ * (call with capacity 0 to size the buffers). */
+int hsb_cpsr_to_csr(int impl, const void *const ch[HSB_NUM_HBM_CHANNELS],
+                    const size_t ch_packets[HSB_NUM_HBM_CHANNELS], unsigned num_row_partitions,
+                    unsigned num_col_partitions, unsigned num_rows, unsigned num_cols, uint32_t *indptr,
+                    uint32_t *indices, uint32_t *vals, size_t capacity, size_t *nnz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HISPARSE_B200_H_ */

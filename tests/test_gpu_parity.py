@@ -1,0 +1,246 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI (include/hisparse_b200.h), against
+  * the oracle restatement (oracle/hsoracle.c) on seeded inputs,
+  * the committed fixtures the reference C simulation produced (tests/golden/), and
+  * the reference's own code (oracle/_ref) when the prebuilt library is present.
+Bit-exact for the fixed-point path; fp32 within 1e-5 norm-wise of the reference CPU SpMV
+(|y - y_ref| <= 1e-5 * sum_i |a_i x_i|, the tolerance BASELINE.json states, made norm-wise so
+that it is meaningful for rows with cancellation)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from hisparse_b200 import capi, matgen
+from oracle import hsoracle
+
+pytestmark = pytest.mark.gpu
+
+FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "csim_*.npz")))
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    if capi.device_count() < 1:
+        pytest.fail("no CUDA device: the GPU tests must run on the B200 box (no CPU fallback exists)")
+    return True
+
+
+def run_fixed_csr(port, mat, x_f32, rows_per_partition=0):
+    rows, cols, indptr, indices, data = mat
+    words = port.quantize(data)
+    xw = port.quantize(x_f32)
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    ctx.upload_matrix_csr(rows, cols, indptr, indices, words, rows_per_partition)
+    ctx.upload_vector(xw)
+    ctx.spmv()
+    y = ctx.download_result()
+    st = ctx.stats()
+    ctx.close()
+    return y, port.spmv_q824(indptr, indices, words, xw), st
+
+
+def check_float(y_words, port, indptr, indices, data, x, extra_ref=None):
+    y = y_words.view(np.float32).astype(np.float64)
+    y64, sa = port.spmv_f64(indptr, indices, data, x)
+    yref = port.spmv_f32(indptr, indices, data, x).astype(np.float64)   # compute_ref restatement
+    bound = TOL * sa + 1e-30
+    assert np.all(np.abs(y - yref) <= bound), float(np.max(np.abs(y - yref) / (sa + 1e-30)))
+    assert np.all(np.abs(y - y64) <= bound)
+
+
+# ------------------------------------------------------------------------------------------
+# fixed point, CSR fast path
+# ------------------------------------------------------------------------------------------
+FIXED_CASES = [
+    ("dense128", lambda: matgen.dense_csr(128, 128), 0, 1.0),
+    ("uniform_1000x1024", lambda: matgen.uniform_sparse_csr(1000, 1024, 10), 0, 1.0),
+    ("rand_4096_1pct", lambda: matgen.random_csr(4096, 4096, 0.01, 0xC0FFEE01), 0, 1.0),
+    ("multi_tile_70000", lambda: matgen.random_csr(900, 70000, 0.003, 7), 0, 1.0),
+    ("rmat_20000", lambda: matgen.rmat_csr(20000, 600000, 8), 0, 1.0),
+    ("rmat_row_partitions", lambda: matgen.rmat_csr(20000, 300000, 9), 4096, 1.0),
+    ("saturating", lambda: matgen.random_csr(512, 3000, 0.2, 10), 0, 60.0),
+    ("more_chunks_than_sms", lambda: matgen.random_csr(3000, 3000, 0.03, 11), 0, 1.0),
+]
+
+
+@pytest.mark.parametrize("name,make,rpp,scale", FIXED_CASES, ids=[c[0] for c in FIXED_CASES])
+def test_fixed_csr_bit_exact(gpu, port, name, make, rpp, scale):
+    rows, cols, indptr, indices, data = make()
+    rng = np.random.default_rng(1)
+    data = (data * np.float32(scale)).astype(np.float32)
+    x = (rng.random(cols, dtype=np.float32) * np.float32(scale)).astype(np.float32)
+    y, want, st = run_fixed_csr(port, (rows, cols, indptr, indices, data), x, rpp)
+    assert np.array_equal(y, want)
+    if name == "saturating":
+        assert (want == 0xFFFFFFFF).any()
+    if rpp:
+        assert st["n_row_parts"] == (rows + rpp - 1) // rpp
+
+
+def test_fixed_edge_cases(gpu, port):
+    # empty matrix, all-empty rows, a single very long row crossing two tiles, x of zeros
+    ip = np.zeros(129, np.uint32)
+    y, want, _ = run_fixed_csr(port, (128, 64, ip, np.zeros(0, np.uint32), np.zeros(0, np.float32)),
+                               np.ones(64, np.float32))
+    assert np.array_equal(y, want) and not y.any()
+    n = 50000
+    ip = np.array([0, 0, n, n, n + 1], np.uint32)
+    ix = np.concatenate([np.arange(n), [3]]).astype(np.uint32)
+    d = np.full(n + 1, 0.001, np.float32)
+    y, want, st = run_fixed_csr(port, (4, n, ip, ix, d), np.full(n, 0.5, np.float32))
+    assert np.array_equal(y, want) and st["n_col_tiles"] == 2
+    y, want, _ = run_fixed_csr(port, (4, n, ip, ix, d), np.zeros(n, np.float32))
+    assert np.array_equal(y, want) and not y.any()
+    # reference-style x in {0,1} (sw/host.cpp:238)
+    rows, cols, indptr, indices, data = matgen.rmat_csr(5000, 80000, 3)
+    x = (np.random.default_rng(0).integers(0, 2, cols)).astype(np.float32)
+    y, want, _ = run_fixed_csr(port, (rows, cols, indptr, indices, data), x)
+    assert np.array_equal(y, want)
+
+
+def test_repeated_runs_and_vector_update(gpu, port):
+    rows, cols, indptr, indices, data = matgen.rmat_csr(8000, 200000, 21)
+    words = port.quantize(data)
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    ctx.upload_matrix_csr(rows, cols, indptr, indices, words)
+    ctx.set_replicas(3)
+    rng = np.random.default_rng(4)
+    for it in range(5):
+        xw = port.quantize(rng.random(cols, dtype=np.float32))
+        ctx.upload_vector(xw)
+        ctx.spmv()
+        assert np.array_equal(ctx.download_result(), port.spmv_q824(indptr, indices, words, xw)), it
+    assert ctx.stats()["kernel_launches"] >= 10
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------
+# fixtures produced by the reference C simulation
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p) for p in FIXTURES])
+@pytest.mark.parametrize("impl", hsoracle.IMPLS)
+def test_reference_fixture_through_cpsr_images(gpu, port, path, impl):
+    """CSR -> reference channel images (oracle restatement of the reference host code) ->
+    hsb_upload_matrix_cpsr -> hsb_spmv_row_partition -> the y the reference csim produced."""
+    g = np.load(path)
+    rows, cols = int(g["rows"]), int(g["cols"])
+    indptr, indices, skip = g["indptr"], g["indices"], bool(g["skip"])
+    cfg = capi.get_config(capi.IMPL_BY_NAME[impl])
+    IF, OB, VB = cfg.interleave_factor, cfg.logical_ob_size, cfg.logical_vb_size
+    data = g["data_" + impl] if ("data_" + impl) in g else g["data"]
+    x = g["x_" + impl] if ("x_" + impl) in g else g["x"]
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128 * IF, 8)
+    assert r2 == int(g[impl + "_rows_padded"])
+    xpad = np.zeros(c2, np.float32)
+    xpad[:cols] = x
+    if impl == "fixed":
+        words, xw, kind = port.quantize(data), port.quantize(xpad), hsoracle.VAL_Q824
+    else:
+        words, xw, kind = data.view(np.uint32), xpad.view(np.uint32), hsoracle.VAL_FLOAT_BITS
+    m = port.csr2cpsr(r2, c2, ip2, indices, words, 8, OB, VB, 16 * IF, skip, kind)
+    images = m.channel_images(IF)
+    ctx = capi.Context(0, impl)
+    ctx.upload_matrix_cpsr(images, m.n_row_parts, m.n_col_parts, r2, c2)
+    ctx.upload_vector(xw)
+    for rp in range(m.n_row_parts):
+        rows_here = OB if (rp < m.n_row_parts - 1 or r2 % OB == 0) else r2 % OB
+        ctx.spmv_row_partition(rp, rows_here // 16, m.n_col_parts, m.n_col_parts * m.n_row_parts, c2)
+    y = ctx.download_result()
+    ctx.close()
+    if impl == "fixed":
+        assert np.array_equal(y, g["fixed_y"])
+    else:
+        check_float(y, port, ip2, indices, data, xpad)
+        # and as close to the reference simulation's own float result
+        _, sa = port.spmv_f64(ip2, indices, data, xpad)
+        yr = g[impl + "_y"].view(np.float32).astype(np.float64)
+        assert np.all(np.abs(y.view(np.float32) - yr) <= 2 * TOL * sa + 1e-30)
+
+
+# ------------------------------------------------------------------------------------------
+# float paths
+# ------------------------------------------------------------------------------------------
+FLOAT_CASES = [
+    ("rand_4096_1pct", lambda: matgen.random_csr(4096, 4096, 0.01, 0xC0FFEE01, values="u01")),
+    ("transformer_like", lambda: matgen.bernoulli_csr(512, 33288, 0.05, 0xC0FFEE03)),
+    ("rmat_20000", lambda: matgen.rmat_csr(20000, 600000, 8, values="normal")),
+]
+
+
+@pytest.mark.parametrize("impl", ["float_pob", "float_stall"])
+@pytest.mark.parametrize("name,make", FLOAT_CASES, ids=[c[0] for c in FLOAT_CASES])
+def test_float_within_tolerance(gpu, port, impl, name, make):
+    rows, cols, indptr, indices, data = make()
+    x = (np.random.default_rng(2).random(cols, dtype=np.float32) * 2 - 1).astype(np.float32)
+    ctx = capi.Context(0, impl)
+    ctx.upload_matrix_csr(rows, cols, indptr, indices, data)
+    ctx.upload_vector(x)
+    ctx.spmv()
+    y = ctx.download_result()
+    ctx.close()
+    check_float(y, port, indptr, indices, data, x)
+
+
+# ------------------------------------------------------------------------------------------
+# drop-in top_wrapper against the reference's own top_wrapper
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", hsoracle.IMPLS)
+def test_top_wrapper_drop_in(gpu, port, impl):
+    if not hsoracle.ref_available(impl):
+        pytest.skip("oracle/_ref not present")
+    ref = hsoracle.Ref(impl)
+    IF, OB, VB = ref.INTERLEAVE_FACTOR, ref.LOGICAL_OB_SIZE, ref.LOGICAL_VB_SIZE
+    rows, cols, indptr, indices, data = matgen.rmat_csr(3000, 40000, 31)
+    if impl != "fixed":
+        data = (data - np.float32(0.5)).astype(np.float32)
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128 * IF, 8)
+    x = np.random.default_rng(6).random(c2, dtype=np.float32)
+    words = ref.val_from_float(data)
+    xw = ref.val_from_float(x)
+    kind = hsoracle.VAL_Q824 if impl == "fixed" else hsoracle.VAL_FLOAT_BITS
+    m = port.csr2cpsr(r2, c2, ip2, indices, words, 8, OB, VB, 16 * IF, True, kind)
+    images = m.channel_images(IF)
+    y_ref = np.zeros(r2, np.uint32)
+    y_gpu = np.zeros(r2, np.uint32)
+    ref.top_wrapper(images, xw, y_ref, 0, r2 // 16, m.n_col_parts, m.n_col_parts, c2)
+    capi.top_wrapper(impl, images, xw, y_gpu, 0, r2 // 16, m.n_col_parts, m.n_col_parts, c2)
+    if impl == "fixed":
+        assert np.array_equal(y_gpu, y_ref)
+    else:
+        _, sa = port.spmv_f64(ip2, indices, data, x)
+        d = np.abs(y_gpu.view(np.float32).astype(np.float64) - y_ref.view(np.float32).astype(np.float64))
+        assert np.all(d <= 2 * TOL * sa + 1e-30)
+
+
+# ------------------------------------------------------------------------------------------
+# full BASELINE size (config C2 stand-in): bit-exact against the closed form + properties
+# ------------------------------------------------------------------------------------------
+def test_fixed_googleplus_size(gpu, port):
+    rows, cols, indptr, indices, data = matgen.rmat_csr(107614, 13_670_000, 0xC0FFEE02)
+    data = (data * np.float32(0.05)).astype(np.float32)
+    data[: indptr[1]] = 200.0                      # make row 0 saturate if it is not empty
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
+    words = port.quantize(data)
+    rng = np.random.default_rng(3)
+    x1 = np.zeros(c2, np.float32)
+    x1[:cols] = rng.integers(0, 2, cols).astype(np.float32)          # reference-style {0,1}
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+    xw = port.quantize(x1)
+    ctx.upload_vector(xw)
+    ctx.spmv()
+    y1 = ctx.download_result()
+    assert np.array_equal(y1, port.spmv_q824(ip2, indices, words, xw))
+    # idempotence: the same launch again gives the same bits (accumulators are re-zeroed)
+    ctx.spmv()
+    assert np.array_equal(ctx.download_result(), y1)
+    # monotonicity property of the unsigned fixed path: x <= x' element-wise  =>  y <= y'
+    xw2 = port.quantize(np.minimum(x1 + rng.random(c2, dtype=np.float32), 255).astype(np.float32))
+    ctx.upload_vector(xw2)
+    ctx.spmv()
+    y2 = ctx.download_result()
+    assert np.all(y2 >= y1)
+    assert np.array_equal(y2, port.spmv_q824(ip2, indices, words, xw2))
+    ctx.close()

@@ -1,0 +1,111 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol
+include/hisparse_b200.h declares, the tile-stream format round-trips, and reference channel
+images decode back to the CSR they were built from. No compute calls (no GPU here)."""
+import numpy as np
+import pytest
+
+from hisparse_b200 import capi, matgen
+from oracle import hsoracle
+
+
+def test_library_exports_every_declared_symbol():
+    capi.build()
+    L = capi.lib()
+    names = capi.declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), n
+    assert b"sm_100a" in L.hsb_version()
+
+
+def test_config_matches_reference_constants(refs):
+    for name, impl in capi.IMPL_BY_NAME.items():
+        cfg = capi.get_config(impl)
+        r = refs[name]
+        assert (cfg.pack_size, cfg.num_hbm_channels, cfg.interleave_factor, cfg.logical_ob_size,
+                cfg.logical_vb_size) == (r.PACK_SIZE, r.NUM_HBM_CHANNELS, r.INTERLEAVE_FACTOR,
+                                         r.LOGICAL_OB_SIZE, r.LOGICAL_VB_SIZE)
+
+
+def test_no_cpu_fallback():
+    """Without a usable GPU the product refuses to run instead of computing on the CPU."""
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.HsbError):
+        capi.Context(0, capi.IMPL_FIXED)
+
+
+def _canon(rows, indptr, indices, vals):
+    """sort entries inside every row by (column, value) for order-insensitive comparison"""
+    r = np.repeat(np.arange(rows, dtype=np.int64), np.diff(indptr.astype(np.int64)))
+    o = np.lexsort((vals, indices, r))
+    return indices[o], vals[o]
+
+
+CASES = [
+    ("empty", (8, 8, np.zeros(9, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.float32)), 0, 0),
+    ("dense", matgen.dense_csr(64, 72), 0, 0),
+    ("uniform_unsorted_cols", matgen.uniform_sparse_csr(1000, 1024, 10), 0, 0),
+    ("rand_multi_tile", matgen.random_csr(300, 70000, 0.004, 3), 0, 0),
+    ("rand_small_tiles", matgen.random_csr(2000, 3000, 0.01, 4), 512, 64),
+    ("rmat_row_parts", matgen.rmat_csr(6000, 90000, 5), 1024, 1024),
+    ("one_long_row", (4, 40000, np.array([0, 0, 40000, 40000, 40001], np.uint32),
+                      np.concatenate([np.arange(40000), [7]]).astype(np.uint32),
+                      np.arange(40001, dtype=np.float32)), 0, 0),
+]
+
+
+@pytest.mark.parametrize("name,mat,rpp,tile", CASES, ids=[c[0] for c in CASES])
+def test_tile_format_round_trip(name, mat, rpp, tile):
+    rows, cols, indptr, indices, data = mat
+    f = capi.Format(rows, cols, indptr, indices, data, rpp, tile)
+    st = f.stats()
+    assert st["nnz"] == indices.size and st["rows"] == rows
+    ip, ix, vv = f.expand()
+    assert np.array_equal(ip, indptr)
+    a = _canon(rows, indptr, indices, np.ascontiguousarray(data).view(np.uint32))
+    b = _canon(rows, ip, ix, vv)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # bytes: 6 per non-zero slot + 4 per segment + 8 per chunk (+ tile table)
+    assert st["format_bytes"] >= 6 * st["nnz"]
+    assert st["n_segments"] <= max(1, rows * st["n_col_tiles"])
+
+
+def test_format_rejects_malformed():
+    ip = np.array([0, 2, 1], np.uint32)
+    with pytest.raises(capi.HsbError):
+        capi.Format(2, 4, ip, np.zeros(2, np.uint32), np.zeros(2, np.float32))
+    ip = np.array([0, 1, 2], np.uint32)
+    with pytest.raises(capi.HsbError):
+        capi.Format(2, 4, ip, np.array([0, 9], np.uint32), np.zeros(2, np.float32))
+
+
+@pytest.mark.parametrize("impl", hsoracle.IMPLS)
+@pytest.mark.parametrize("skip", [False, True])
+def test_cpsr_images_decode_to_original_csr(port, impl, skip):
+    """reference-format channel images (built by the oracle's restatement of sw/host.cpp:163-231,
+    itself pinned against the reference) -> hsb_cpsr_to_csr == the CSR we started from."""
+    cfg = capi.get_config(capi.IMPL_BY_NAME[impl])
+    IF = cfg.interleave_factor
+    rows, cols, indptr, indices, data = matgen.rmat_csr(4000, 50000, 17)
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128 * IF, 8)
+    words = port.quantize(data) if impl == "fixed" else data.view(np.uint32)
+    kind = hsoracle.VAL_Q824 if impl == "fixed" else hsoracle.VAL_FLOAT_BITS
+    m = port.csr2cpsr(r2, c2, ip2, indices, words, 8, cfg.logical_ob_size, cfg.logical_vb_size, 16 * IF, skip, kind)
+    images = m.channel_images(IF)
+    ip, ix, vv = capi.cpsr_to_csr(impl, images, m.n_row_parts, m.n_col_parts, r2, c2)
+    assert np.array_equal(ip, ip2)
+    a = _canon(r2, ip2, indices, words)
+    b = _canon(r2, ip, ix, vv)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_cpsr_decode_rejects_truncated_image(port):
+    cfg = capi.get_config(0)
+    rows, cols, indptr, indices, data = matgen.random_csr(256, 512, 0.05, 9)
+    m = port.csr2cpsr(rows, cols, indptr, indices, port.quantize(data), 8, cfg.logical_ob_size,
+                      cfg.logical_vb_size, 16, False, hsoracle.VAL_Q824)
+    images = m.channel_images(1)
+    images[3] = images[3][:-1]
+    with pytest.raises(capi.HsbError):
+        capi.cpsr_to_csr(0, images, 1, 1, rows, cols)
