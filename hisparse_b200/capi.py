@@ -32,8 +32,8 @@ class Config(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("nnz", C.c_uint64), ("rows", C.c_uint32), ("cols", C.c_uint32), ("n_row_parts", C.c_uint32),
-                ("n_col_tiles", C.c_uint32), ("tile_cols", C.c_uint32), ("n_chunks", C.c_uint64),
-                ("n_segments", C.c_uint64), ("format_bytes", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
+                ("n_col_tiles", C.c_uint32), ("tile_cols", C.c_uint32), ("n_slices", C.c_uint64),
+                ("n_streams", C.c_uint64), ("n_elems", C.c_uint64), ("format_bytes", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("sm_count", C.c_uint32), ("grid", C.c_uint32),
                 ("replicas", C.c_uint32), ("preprocess_seconds", C.c_double)]
 
@@ -94,6 +94,7 @@ def lib():
     for n in ("hsb_device_x", "hsb_device_y", "hsb_stream"):
         getattr(L, n).argtypes = [vp]
         getattr(L, n).restype = vp
+    L.hsb_debug_trace.argtypes = [vp, vp, sz]
     L.hsb_format_build.argtypes = [u32, u32, vp, vp, vp, u32, u32]
     L.hsb_format_build.restype = vp
     L.hsb_format_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -223,6 +224,17 @@ class Context:
         a, b = C.c_float(), C.c_float()
         _check(lib().hsb_time_spmv(self.h, warmup, steps, C.byref(a), C.byref(b) if kernel else None))
         return a.value, (b.value if kernel else None)
+
+    def trace(self, arm=None):
+        """arm=True/False switches tracing; arm=None returns the [sm_count, 34] stamps of the last launch"""
+        if arm is not None:
+            return lib().hsb_debug_trace(self.h, None, 1 if arm else 0)
+        n = lib().hsb_debug_trace(self.h, None, 1)
+        out = np.zeros(n, np.uint64)
+        rc = lib().hsb_debug_trace(self.h, _ptr(out), n)
+        if rc < 0:
+            _check(rc)
+        return out.reshape(-1, 34)
 
     def device_x(self):
         return lib().hsb_device_x(self.h)

@@ -34,13 +34,12 @@ int set_err(int code, const std::string &m) { g_err = m; return code; }
 
 struct DeviceMatrix {
     uint32_t *vals = nullptr;
-    uint16_t *cidx = nullptr;
-    hsb::ChunkDesc *chunks = nullptr;
+    uint16_t *cols = nullptr;
+        uint32_t *slice_rows = nullptr;
     hsb::TileDesc *tiles = nullptr;
-    uint32_t *seg_row = nullptr;
     void release() {
-        cudaFree(vals); cudaFree(cidx); cudaFree(chunks); cudaFree(tiles); cudaFree(seg_row);
-        vals = nullptr; cidx = nullptr; chunks = nullptr; tiles = nullptr; seg_row = nullptr;
+        cudaFree(vals); cudaFree(cols); cudaFree(slice_rows); cudaFree(tiles);
+        vals = nullptr; cols = nullptr; slice_rows = nullptr; tiles = nullptr;
     }
 };
 
@@ -56,15 +55,25 @@ struct hsb_ctx {
     uint32_t rows = 0, cols = 0, x_words = 0;
     uint64_t nnz = 0;
     uint32_t rows_per_part = 0, n_row_parts = 0, n_col_tiles = 0, tile_cols = 0;
-    uint64_t n_chunks = 0, n_segments = 0, format_bytes = 0;
-    std::vector<uint32_t> part_chunk_begin;
+    uint64_t n_slices = 0, n_streams = 0, n_elems = 0, format_bytes = 0;
+    std::vector<uint32_t> part_slice_begin;
     std::vector<DeviceMatrix> mats;       // [0] + replicas
-    size_t sz_vals = 0, sz_cidx = 0, sz_chunks = 0, sz_tiles = 0, sz_seg = 0;
+    size_t sz_vals = 0, sz_cols = 0, sz_rows = 0, sz_tiles = 0;
     unsigned next_replica = 0;
+    // launch plans: slot 0 = whole matrix, slot 1 + j = row partition j
+    uint32_t *d_cta_seg = nullptr;        // [slots][sm_count + 1]
+    hsb::Segment *d_segs = nullptr;
+    std::vector<uint32_t> plan_grid;      // CTAs used by each of those launches
     // vectors
     uint32_t *d_x = nullptr;              // x_words words (padded to whole tiles, zero filled)
     uint32_t *d_y = nullptr;              // rows words
-    unsigned long long *d_acc = nullptr;  // fixed: 64-bit row accumulators
+    // rows + 1 accumulators (uint64 fixed / fp32 float) x 2: a launch adds into one buffer while it
+    // drains the other (the previous launch's sums) into y
+    void *d_acc[2] = {nullptr, nullptr};
+    int acc_cur = 0;
+    bool drain_pending = false;           // d_acc[acc_cur ^ 1] holds sums that are not in y yet
+    uint32_t drain_begin = 0, drain_end = 0;
+    unsigned long long *d_trace = nullptr; // optional per-warp clock stamps of the last launch
     uint64_t launches = 0;
     double preprocess_s = 0;
 };
@@ -74,76 +83,111 @@ namespace {
 void free_matrix(hsb_ctx *c) {
     for (auto &m : c->mats) m.release();
     c->mats.clear();
-    cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_acc);
-    c->d_x = nullptr; c->d_y = nullptr; c->d_acc = nullptr;
+    cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_acc[0]); cudaFree(c->d_acc[1]); cudaFree(c->d_cta_seg); cudaFree(c->d_segs);
+    c->d_x = nullptr; c->d_y = nullptr; c->d_acc[0] = c->d_acc[1] = nullptr; c->d_cta_seg = nullptr; c->d_segs = nullptr;
+    c->drain_pending = false; c->acc_cur = 0;
     c->have_matrix = false;
 }
 
 int upload_tiled(hsb_ctx *c, const hsb::TiledMatrix &M) {
     CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     free_matrix(c);
     c->rows = M.rows; c->cols = M.cols; c->nnz = M.nnz;
     c->rows_per_part = M.rows_per_part; c->n_row_parts = M.n_row_parts;
     c->n_col_tiles = M.n_col_tiles; c->tile_cols = M.tile_cols;
-    c->n_chunks = M.n_chunks(); c->n_segments = M.seg_row.size(); c->format_bytes = M.format_bytes();
-    c->part_chunk_begin = M.part_chunk_begin;
-    c->sz_vals = M.vals.size() * 4; c->sz_cidx = M.cidx.size() * 2;
-    c->sz_chunks = M.chunks.size() * sizeof(hsb::ChunkDesc); c->sz_tiles = M.tiles.size() * sizeof(hsb::TileDesc);
-    c->sz_seg = M.seg_row.size() * 4;
+    c->n_slices = M.n_slices(); c->n_streams = M.n_streams; c->n_elems = M.n_elems();
+    c->format_bytes = M.format_bytes();
+    c->part_slice_begin = M.part_slice_begin;
+    c->sz_vals = M.vals.size() * 4; c->sz_cols = M.cols16.size() * 2;
+    c->sz_rows = M.slice_rows.size() * 4;
+    c->sz_tiles = M.tiles.size() * sizeof(hsb::TileDesc);
     DeviceMatrix d;
     CUDA_TRY(cudaMalloc(&d.vals, c->sz_vals + 16));
-    CUDA_TRY(cudaMalloc(&d.cidx, c->sz_cidx + 16));
-    CUDA_TRY(cudaMalloc(&d.chunks, c->sz_chunks + 16));
+    CUDA_TRY(cudaMalloc(&d.cols, c->sz_cols + 16));
+    CUDA_TRY(cudaMalloc(&d.slice_rows, c->sz_rows + 16));
     CUDA_TRY(cudaMalloc(&d.tiles, c->sz_tiles + 16));
-    CUDA_TRY(cudaMalloc(&d.seg_row, c->sz_seg + 16));
     CUDA_TRY(cudaMemcpyAsync(d.vals, M.vals.data(), c->sz_vals, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(d.cidx, M.cidx.data(), c->sz_cidx, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(d.chunks, M.chunks.data(), c->sz_chunks, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.cols, M.cols16.data(), c->sz_cols, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.slice_rows, M.slice_rows.data(), c->sz_rows, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(d.tiles, M.tiles.data(), c->sz_tiles, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(d.seg_row, M.seg_row.data(), c->sz_seg, cudaMemcpyHostToDevice, c->stream));
     c->mats.push_back(d);
+    // cost-balanced work plans for the whole-matrix launch and for each row partition
+    const uint32_t G = (uint32_t)c->sm_count, T = M.n_col_tiles;
+    std::vector<uint32_t> cta_seg_all;
+    std::vector<hsb::Segment> segs;
+    c->plan_grid.assign(1 + M.n_row_parts, 1);
+    auto plan = [&](size_t slot, uint32_t tile0, uint32_t tile1) {
+        uint64_t steps = 0;
+        for (uint32_t t = tile0; t < tile1; t++) steps += M.tiles[t].slice_end - M.tiles[t].slice_begin;
+        uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(G, steps));   // >= one slice per CTA
+        c->plan_grid[slot] = g;
+        std::vector<uint32_t> cs;
+        hsb::plan_launch(M, tile0, tile1, g, &cs, &segs);
+        cs.resize(G + 1, cs.back());
+        cta_seg_all.insert(cta_seg_all.end(), cs.begin(), cs.end());
+    };
+    plan(0, 0, M.n_row_parts * T);
+    for (uint32_t j = 0; j < M.n_row_parts; j++) plan(1 + j, j * T, (j + 1) * T);
+    CUDA_TRY(cudaMalloc(&c->d_cta_seg, cta_seg_all.size() * 4));
+    CUDA_TRY(cudaMemcpyAsync(c->d_cta_seg, cta_seg_all.data(), cta_seg_all.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMalloc(&c->d_segs, (segs.size() + 1) * sizeof(hsb::Segment)));
+    CUDA_TRY(cudaMemcpyAsync(c->d_segs, segs.data(), segs.size() * sizeof(hsb::Segment), cudaMemcpyHostToDevice, c->stream));
     // x is padded to whole tiles so that every bulk copy of a tile stays inside the buffer
     c->x_words = M.n_col_tiles * M.tile_cols;
     CUDA_TRY(cudaMalloc(&c->d_x, (size_t)c->x_words * 4 + 16));
     CUDA_TRY(cudaMemsetAsync(c->d_x, 0, (size_t)c->x_words * 4, c->stream));
     CUDA_TRY(cudaMalloc(&c->d_y, (size_t)std::max(c->rows, 1u) * 4));
     CUDA_TRY(cudaMemsetAsync(c->d_y, 0, (size_t)std::max(c->rows, 1u) * 4, c->stream));
-    if (c->arith == hsb::kArithFixed) CUDA_TRY(cudaMalloc(&c->d_acc, (size_t)std::max(c->rows, 1u) * 8));
+    const size_t esz = c->arith == hsb::kArithFixed ? 8 : 4;
+    for (int b = 0; b < 2; b++) {
+        CUDA_TRY(cudaMalloc(&c->d_acc[b], ((size_t)c->rows + 1) * esz));
+        CUDA_TRY(cudaMemsetAsync(c->d_acc[b], 0, ((size_t)c->rows + 1) * esz, c->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    c->grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count, c->n_chunks));
+    c->grid = (int)c->plan_grid[0];
     c->next_replica = 0;
     c->have_matrix = true;
     return HSB_OK;
 }
 
-// one SpMV over chunk range [cb, ce) / rows [rb, re); optional event pair around the tile kernel
-int run_range(hsb_ctx *c, uint32_t cb, uint32_t ce, uint32_t rb, uint32_t re, cudaEvent_t k0, cudaEvent_t k1) {
+// one launch = one SpMV over the slices of `slot` (0: whole matrix, 1 + j: row partition j), rows [rb, re)
+int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, cudaEvent_t k1) {
     const DeviceMatrix &m = c->mats[c->next_replica % c->mats.size()];
     c->next_replica++;
-    void *acc = c->arith == hsb::kArithFixed ? (void *)c->d_acc : (void *)c->d_y;
-    size_t esz = c->arith == hsb::kArithFixed ? 8 : 4;
-    if (re > rb) CUDA_TRY(cudaMemsetAsync((char *)acc + (size_t)rb * esz, 0, (size_t)(re - rb) * esz, c->stream));
+    const uint32_t G = (uint32_t)c->sm_count;
+    const int grid = (int)c->plan_grid[slot];
     hsb::SpmvParams p;
-    p.vals = m.vals; p.cidx = m.cidx; p.chunks = m.chunks; p.tiles = m.tiles; p.seg_row = m.seg_row;
-    p.x = c->d_x; p.acc = acc; p.chunk_begin = cb; p.chunk_end = ce;
+    p.vals = m.vals; p.cols = m.cols; p.slice_rows = m.slice_rows; p.tiles = m.tiles;
+    p.cta_seg = c->d_cta_seg + slot * (size_t)(G + 1);
+    p.segs = c->d_segs;
+    p.x = c->d_x; p.y = c->d_y;
+    p.acc = c->d_acc[c->acc_cur];
+    p.drain_acc = c->drain_pending ? c->d_acc[c->acc_cur ^ 1] : nullptr;
+    p.drain_begin = c->drain_begin; p.drain_end = c->drain_end;
+    p.trash_row = c->rows;
+    p.trace = c->d_trace;
     if (k0) CUDA_TRY(cudaEventRecord(k0, c->stream));
-    if (ce > cb) {
-        int grid = (int)std::min<uint64_t>((uint64_t)c->grid, ce - cb);
-        hsb::launch_spmv_tiles(c->arith, p, grid, c->stream);
-        c->launches++;
-    }
+    CUDA_TRY(hsb::launch_spmv(c->arith, p, grid, c->stream));
+    c->launches++;
     if (k1) CUDA_TRY(cudaEventRecord(k1, c->stream));
-    if (c->arith == hsb::kArithFixed && re > rb) {
-        hsb::launch_finalize_fixed(c->d_acc, c->d_y, rb, re, c->stream);
-        c->launches++;
-    }
-    CUDA_TRY(cudaGetLastError());
+    c->drain_pending = true;
+    c->drain_begin = rb; c->drain_end = re;
+    c->acc_cur ^= 1;
     return HSB_OK;
 }
 
-int run_all(hsb_ctx *c, cudaEvent_t k0, cudaEvent_t k1) {
-    return run_range(c, 0, (uint32_t)c->n_chunks, 0, c->rows, k0, k1);
+// make y final: drain what the last launch accumulated (stream-ordered, no host sync)
+int finish(hsb_ctx *c) {
+    if (!c->drain_pending) return HSB_OK;
+    CUDA_TRY(hsb::launch_drain(c->arith, c->d_acc[c->acc_cur ^ 1], c->d_y, c->drain_begin, c->drain_end, c->rows,
+                               c->stream));
+    c->launches++;
+    c->drain_pending = false;
+    return HSB_OK;
 }
+
+int run_all(hsb_ctx *c, cudaEvent_t k0, cudaEvent_t k1) { return run_slot(c, 0, 0, c->rows, k0, k1); }
 
 }  // namespace
 
@@ -208,6 +252,7 @@ void hsb_destroy(hsb_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_matrix(c);
+    cudaFree(c->d_trace);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -280,7 +325,7 @@ int hsb_spmv_row_partition(hsb_ctx *c, unsigned row_part_id, unsigned part_len, 
     if (num_cols < c->cols || num_cols > c->x_words || (num_col_partitions && num_partitions % num_col_partitions))
         return set_err(HSB_EINVAL, "num_cols / partition counts do not match the matrix");
     CUDA_TRY(cudaSetDevice(c->device));
-    return run_range(c, c->part_chunk_begin[row_part_id], c->part_chunk_begin[row_part_id + 1], rb, re, nullptr, nullptr);
+    return run_slot(c, 1 + row_part_id, rb, re, nullptr, nullptr);
 }
 
 int hsb_spmv(hsb_ctx *c) {
@@ -293,6 +338,7 @@ int hsb_spmv(hsb_ctx *c) {
 int hsb_sync(hsb_ctx *c) {
     if (!c) return set_err(HSB_EINVAL, "null context");
     CUDA_TRY(cudaSetDevice(c->device));
+    if (c->have_matrix) { int rc = finish(c); if (rc) return rc; }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return HSB_OK;
 }
@@ -302,6 +348,7 @@ int hsb_download_result(hsb_ctx *c, void *y_packed, unsigned num_rows) {
     if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
     if (num_rows > c->rows) return set_err(HSB_EINVAL, "num_rows exceeds the matrix");
     CUDA_TRY(cudaSetDevice(c->device));
+    { int rc = finish(c); if (rc) return rc; }
     CUDA_TRY(cudaMemcpyAsync(y_packed, c->d_y, (size_t)num_rows * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return HSB_OK;
@@ -346,7 +393,8 @@ int hsb_get_stats(hsb_ctx *c, hsb_stats *out) {
     std::memset(out, 0, sizeof *out);
     out->nnz = c->nnz; out->rows = c->rows; out->cols = c->cols;
     out->n_row_parts = c->n_row_parts; out->n_col_tiles = c->n_col_tiles; out->tile_cols = c->tile_cols;
-    out->n_chunks = c->n_chunks; out->n_segments = c->n_segments; out->format_bytes = c->format_bytes;
+    out->n_slices = c->n_slices; out->n_streams = c->n_streams; out->n_elems = c->n_elems;
+    out->format_bytes = c->format_bytes;
     out->algorithmic_bytes = 8ull * c->nnz + 4ull * ((uint64_t)c->rows + 1) + 4ull * c->rows + 4ull * c->cols;
     out->kernel_launches = c->launches; out->sm_count = c->sm_count; out->grid = c->grid;
     out->replicas = (uint32_t)c->mats.size(); out->preprocess_seconds = c->preprocess_s;
@@ -362,15 +410,13 @@ int hsb_set_replicas(hsb_ctx *c, int n) {
         DeviceMatrix d;
         const DeviceMatrix &s = c->mats[0];
         CUDA_TRY(cudaMalloc(&d.vals, c->sz_vals + 16));
-        CUDA_TRY(cudaMalloc(&d.cidx, c->sz_cidx + 16));
-        CUDA_TRY(cudaMalloc(&d.chunks, c->sz_chunks + 16));
+        CUDA_TRY(cudaMalloc(&d.cols, c->sz_cols + 16));
+            CUDA_TRY(cudaMalloc(&d.slice_rows, c->sz_rows + 16));
         CUDA_TRY(cudaMalloc(&d.tiles, c->sz_tiles + 16));
-        CUDA_TRY(cudaMalloc(&d.seg_row, c->sz_seg + 16));
         CUDA_TRY(cudaMemcpyAsync(d.vals, s.vals, c->sz_vals, cudaMemcpyDeviceToDevice, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(d.cidx, s.cidx, c->sz_cidx, cudaMemcpyDeviceToDevice, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(d.chunks, s.chunks, c->sz_chunks, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(d.cols, s.cols, c->sz_cols, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(d.slice_rows, s.slice_rows, c->sz_rows, cudaMemcpyDeviceToDevice, c->stream));
         CUDA_TRY(cudaMemcpyAsync(d.tiles, s.tiles, c->sz_tiles, cudaMemcpyDeviceToDevice, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(d.seg_row, s.seg_row, c->sz_seg, cudaMemcpyDeviceToDevice, c->stream));
         c->mats.push_back(d);
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -385,9 +431,11 @@ int hsb_time_spmv(hsb_ctx *c, int warmup, int steps, float *step_ms, float *kern
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
     for (int i = 0; i < warmup; i++) { int rc = run_all(c, nullptr, nullptr); if (rc) return rc; }
+    { int rc = finish(c); if (rc) return rc; }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaEventRecord(e0, c->stream));
     for (int i = 0; i < steps; i++) { int rc = run_all(c, nullptr, nullptr); if (rc) return rc; }
+    { int rc = finish(c); if (rc) return rc; }            // the last drain belongs to the timed work
     CUDA_TRY(cudaEventRecord(e1, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     float ms = 0;
@@ -406,6 +454,27 @@ int hsb_time_spmv(hsb_ctx *c, int warmup, int steps, float *step_ms, float *kern
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return HSB_OK;
+}
+
+int hsb_debug_trace(hsb_ctx *c, unsigned long long *out, size_t capacity) {
+    if (!c) return set_err(HSB_EINVAL, "null context");
+    const size_t n = (size_t)c->sm_count * (hsb::kWarps + 2);
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!out) {                                   // arm (or disarm with capacity == 0)
+        if (capacity && !c->d_trace) {
+            CUDA_TRY(cudaMalloc(&c->d_trace, n * 8));
+            CUDA_TRY(cudaMemset(c->d_trace, 0, n * 8));
+        } else if (!capacity && c->d_trace) {
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_trace);
+            c->d_trace = nullptr;
+        }
+        return (int)n;
+    }
+    if (!c->d_trace || capacity < n) return set_err(HSB_ESTATE, "trace not armed or buffer too small");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(out, c->d_trace, n * 8, cudaMemcpyDeviceToHost));
+    return (int)n;
 }
 
 void *hsb_device_x(hsb_ctx *c) { return c ? c->d_x : nullptr; }

@@ -32,8 +32,8 @@ int hsb_format_stats(const hsb_format *f, hsb_stats *out) {
     std::memset(out, 0, sizeof *out);
     const hsb::TiledMatrix &M = f->M;
     out->nnz = M.nnz; out->rows = M.rows; out->cols = M.cols; out->n_row_parts = M.n_row_parts;
-    out->n_col_tiles = M.n_col_tiles; out->tile_cols = M.tile_cols; out->n_chunks = M.n_chunks();
-    out->n_segments = M.seg_row.size(); out->format_bytes = M.format_bytes();
+    out->n_col_tiles = M.n_col_tiles; out->tile_cols = M.tile_cols; out->n_slices = M.n_slices();
+    out->n_streams = M.n_streams; out->n_elems = M.n_elems(); out->format_bytes = M.format_bytes();
     out->algorithmic_bytes = 8ull * M.nnz + 4ull * ((uint64_t)M.rows + 1) + 4ull * M.rows + 4ull * M.cols;
     return HSB_OK;
 }
@@ -41,9 +41,11 @@ int hsb_format_stats(const hsb_format *f, hsb_stats *out) {
 int hsb_format_expand(const hsb_format *f, uint32_t *indptr, uint32_t *indices, uint32_t *vals) {
     if (!f || !indptr) return HSB_EINVAL;
     const hsb::TiledMatrix &M = f->M;
-    // pass 0 counts per row, pass 1 places; both walk chunk by chunk, lane by lane, like the kernel
+    // pass 0 counts per row, pass 1 places; both walk slice by slice, lane by lane, with the very
+    // address arithmetic the kernel uses (slice_elem == the warp's vector-load pattern)
     std::vector<uint32_t> cursor;
     std::fill(indptr, indptr + M.rows + 1, 0u);
+    uint64_t streams_seen = 0;
     for (int pass = 0; pass < 2; pass++) {
         if (pass == 1) {
             for (uint32_t r = 0; r < M.rows; r++) indptr[r + 1] += indptr[r];
@@ -52,50 +54,46 @@ int hsb_format_expand(const hsb_format *f, uint32_t *indptr, uint32_t *indices, 
         }
         for (size_t ti = 0; ti < M.tiles.size(); ti++) {
             const hsb::TileDesc &td = M.tiles[ti];
-            uint32_t row_lo = td.row_part * M.rows_per_part;
-            for (uint32_t c = td.chunk_begin; c < td.chunk_end; c++) {
-                const hsb::ChunkDesc &cd = M.chunks[c];
-                if ((cd.tile & ~hsb::kChunkContinues) != ti) return HSB_EINVAL;
-                uint32_t seg = cd.seg_base;
-                int last_flag = -1, last_real = -1;
-                for (int lane = 0; lane < hsb::kLanes; lane++)
-                    for (int k = 0; k < hsb::kNnzPerLane; k++) {
-                        int j = lane * hsb::kNnzPerLane + k;
-                        uint16_t w = M.cidx[(size_t)c * hsb::kChunkNnz + j];
-                        uint32_t v = M.vals[(size_t)c * hsb::kChunkNnz + hsb::val_slot(lane, k)];
-                        bool flag = w & hsb::kSegEndFlag;
-                        // padding: after the tile's last flag (zero value, zero column, no flag)
-                        bool is_pad = !(cd.tile & hsb::kChunkContinues) && !flag && [&] {
-                            for (int q = j; q < hsb::kChunkNnz; q++)
-                                if (M.cidx[(size_t)c * hsb::kChunkNnz + q] & hsb::kSegEndFlag) return false;
-                            return true;
-                        }();
-                        if (is_pad) {
-                            if (w || v) return HSB_EINVAL;
+            const uint32_t row_lo = td.row_part * M.rows_per_part;
+            uint32_t prev_steps = 0xFFFFFFFFu;
+            for (uint32_t s = td.slice_begin; s < td.slice_end; s++) {
+                const hsb::SliceDesc &sd = M.slices[s];
+                if ((sd.tile_steps >> 8) != ti) return HSB_EINVAL;
+                const uint32_t steps = sd.tile_steps & 0xFFu;
+                if (steps == 0 || steps > hsb::kMaxStreamLen / hsb::kSlotBlock || steps > prev_steps) return HSB_EINVAL;
+                prev_steps = steps;                                  // sorted by length inside a tile
+                const size_t base = (size_t)sd.off * hsb::kStepElems;
+                if (base + (size_t)steps * hsb::kStepElems > M.vals.size()) return HSB_EINVAL;
+                for (int lane = 0; lane < hsb::kLanes; lane++) {
+                    const uint32_t row = M.slice_rows[(size_t)s * hsb::kLanes + lane];
+                    bool ended = false;
+                    uint32_t len = 0;
+                    for (uint32_t k = 0; k < steps * hsb::kSlotBlock; k++) {
+                        const size_t e = hsb::slice_elem(base, lane, k);
+                        const uint16_t c16 = M.cols16[e];
+                        if (c16 == hsb::kPadCol) {                   // padding: zero value, and only at the tail
+                            if (M.vals[e]) return HSB_EINVAL;
+                            ended = true;
                             continue;
                         }
-                        last_real = j;
-                        if (seg >= M.seg_row.size()) return HSB_EINVAL;
-                        uint32_t row = M.seg_row[seg];
-                        if (row < row_lo || row >= M.rows) return HSB_EINVAL;
-                        uint32_t col = td.col_base + (w & 0x7FFFu);
-                        if ((w & 0x7FFFu) >= td.col_count || col >= M.cols) return HSB_EINVAL;
+                        if (ended || row >= M.rows || row < row_lo) return HSB_EINVAL;
+                        if (c16 >= td.col_count || td.col_base + c16 >= M.cols) return HSB_EINVAL;
+                        len++;
                         if (pass == 0) {
                             indptr[row + 1]++;
                         } else {
                             uint32_t at = cursor[row]++;
-                            indices[at] = col;
-                            vals[at] = v;
+                            indices[at] = td.col_base + c16;
+                            vals[at] = M.vals[e];
                         }
-                        if (flag) { seg++; last_flag = j; }
                     }
-                bool cont = last_real > last_flag;
-                if (cont != bool(cd.tile & hsb::kChunkContinues)) return HSB_EINVAL;
-                if (c + 1 < td.chunk_end && M.chunks[c + 1].seg_base != seg) return HSB_EINVAL;
+                    if (row == M.rows && len) return HSB_EINVAL;     // unused lanes hold nothing
+                    if (pass == 0 && len) streams_seen++;
+                }
             }
         }
     }
-    return HSB_OK;
+    return streams_seen == M.n_streams ? HSB_OK : HSB_EINVAL;
 }
 
 void hsb_format_free(hsb_format *f) { delete f; }

@@ -1,11 +1,13 @@
-// sm_100a SpMV kernels. See spmv_kernels.cuh for the mapping to the reference's units.
+// sm_100a SpMV kernel. See spmv_kernels.cuh for the mapping to the reference's units.
 #include "spmv_kernels.cuh"
+
+#include <algorithm>
 
 namespace hsb {
 namespace {
 
 // ---------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + TMA bulk copy (cp.async.bulk -> UBLKCP), streaming 128-bit loads
+// PTX helpers: mbarrier + TMA bulk copy (cp.async.bulk -> UBLKCP), streaming vector loads
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -34,123 +36,185 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+__device__ __forceinline__ uint4 ldg_stream128(const uint4 *p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
-__device__ __forceinline__ uint2 ldg_desc(const ChunkDesc *p) {
+__device__ __forceinline__ uint2 ldg_stream64(const uint2 *p) {
     uint2 r;
-    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
-
 // ---------------------------------------------------------------------------------------
 // arithmetic policies
 // ---------------------------------------------------------------------------------------
 struct FixedArith {                                   // ap_ufixed<32,8,AP_RND,AP_SAT>
     typedef unsigned long long acc_t;
-    static __device__ __forceinline__ acc_t zero() { return 0ull; }
-    static __device__ __forceinline__ acc_t mac(acc_t acc, uint32_t a, uint32_t x) {
-        unsigned long long p = (unsigned long long)a * (unsigned long long)x;      // exact, 48 fraction bits
-        p = (p + (1ull << 23)) >> 24;                                              // AP_RND
-        p = (p >> 32) ? 0xFFFFFFFFull : p;                                         // AP_SAT of the product
-        return acc + p;                                                            // exact; clamp deferred
+    // a lane stream has <= 128 terms: the high part (<= 2^24 each) and the low part (< 2^8 each)
+    // of the rounded products are summed separately in 32 bits and recombined exactly
+    uint32_t hi, lo;
+    __device__ __forceinline__ void clear() { hi = 0; lo = 0; }
+    __device__ __forceinline__ void mac(uint32_t a, uint32_t x) {
+        unsigned long long q = (unsigned long long)a * x + 0x800000ull;   // exact product + half LSB (AP_RND)
+        // (q >> 24) = (q.hi << 8) + (q.lo >> 24). A product that saturates (AP_SAT: q.hi >= 2^24) is
+        // replaced by a value >= 2^32, which forces the drain's clamp -- exactly what saturation means
+        // for a sum of non-negative terms.
+        hi += min((uint32_t)(q >> 32), 0x1000000u);
+        lo += (uint32_t)q >> 24;
     }
-    static __device__ __forceinline__ acc_t add(acc_t a, acc_t b) { return a + b; }
+    __device__ __forceinline__ acc_t total() const { return ((acc_t)hi << 8) + lo; }
     static __device__ __forceinline__ void emit(void *acc, uint32_t row, acc_t v) {
         if (v) atomicAdd(reinterpret_cast<unsigned long long *>(acc) + row, v);    // RED.ADD.64
+    }
+    static __device__ __forceinline__ acc_t warp_sum(acc_t v) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        return v;
+    }
+    static __device__ __forceinline__ uint32_t drain(void *acc, uint32_t row) {
+        unsigned long long *p = reinterpret_cast<unsigned long long *>(acc) + row;
+        unsigned long long a = __ldcg(p);
+        *p = 0ull;
+        return (a >> 32) ? 0xFFFFFFFFu : (uint32_t)a;                              // AP_SAT (pe.h:72)
     }
 };
 struct FloatArith {                                   // fp32 multiply, then fp32 add (not fused)
     typedef float acc_t;
-    static __device__ __forceinline__ acc_t zero() { return 0.0f; }
-    static __device__ __forceinline__ acc_t mac(acc_t acc, uint32_t a, uint32_t x) {
-        return __fadd_rn(acc, __fmul_rn(__uint_as_float(a), __uint_as_float(x)));
+    float s;
+    __device__ __forceinline__ void clear() { s = 0.0f; }
+    __device__ __forceinline__ void mac(uint32_t a, uint32_t x) {
+        s = __fadd_rn(s, __fmul_rn(__uint_as_float(a), __uint_as_float(x)));
     }
-    static __device__ __forceinline__ acc_t add(acc_t a, acc_t b) { return __fadd_rn(a, b); }
+    __device__ __forceinline__ acc_t total() const { return s; }
     static __device__ __forceinline__ void emit(void *acc, uint32_t row, acc_t v) {
-        if (v != 0.0f) atomicAdd(reinterpret_cast<float *>(acc) + row, v);         // RED.ADD.F32
+        atomicAdd(reinterpret_cast<float *>(acc) + row, v);                        // RED.ADD.F32
+    }
+    static __device__ __forceinline__ acc_t warp_sum(acc_t v) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
+        return v;
+    }
+    static __device__ __forceinline__ uint32_t drain(void *acc, uint32_t row) {
+        float *p = reinterpret_cast<float *>(acc) + row;
+        float a = __ldcg(p);
+        *p = 0.0f;
+        return __float_as_uint(a);
     }
 };
-
-struct ChunkRegs {
-    uint4 v0, v1;      // 8 value words of this lane
-    uint4 ci;          // 8 x (local column | end-of-segment flag)
-    uint2 desc;        // ChunkDesc
-};
-
-__device__ __forceinline__ void load_chunk(const SpmvParams &p, uint32_t ch, uint32_t lane, ChunkRegs &r) {
-    const uint4 *vp = reinterpret_cast<const uint4 *>(p.vals + (size_t)ch * kChunkNnz);
-    r.v0 = ldg_stream(vp + lane);
-    r.v1 = ldg_stream(vp + kLanes + lane);
-    r.ci = ldg_stream(reinterpret_cast<const uint4 *>(p.cidx + (size_t)ch * kChunkNnz) + lane);
-    r.desc = ldg_desc(p.chunks + ch);
-}
 
 template <class A>
-__device__ __forceinline__ void process_chunk(const SpmvParams &p, const uint32_t *xs, const ChunkRegs &r,
-                                              uint32_t lane) {
-    typedef typename A::acc_t acc_t;
-    const uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t w[kNnzPerLane] = {r.ci.x & 0xFFFFu, r.ci.x >> 16, r.ci.y & 0xFFFFu, r.ci.y >> 16,
-                                     r.ci.z & 0xFFFFu, r.ci.z >> 16, r.ci.w & 0xFFFFu, r.ci.w >> 16};
-    const uint32_t v[kNnzPerLane] = {r.v0.x, r.v0.y, r.v0.z, r.v0.w, r.v1.x, r.v1.y, r.v1.z, r.v1.w};
+__device__ __forceinline__ void mac4(A &acc, const uint32_t *xs, const uint4 &v, const uint2 &c) {
+    acc.mac(v.x, xs[c.x & 0xFFFFu]);
+    acc.mac(v.y, xs[c.x >> 16]);
+    acc.mac(v.z, xs[c.y & 0xFFFFu]);
+    acc.mac(v.w, xs[c.y >> 16]);
+}
 
-    // gather x from the shared-memory tile (the vecbuf_reader step)
-    uint32_t xv[kNnzPerLane];
-#pragma unroll
-    for (int k = 0; k < kNnzPerLane; k++) xv[k] = xs[w[k] & 0x7FFFu];
-
-    // how many segments end in lanes before this one
-    uint32_t nfl = 0;
-#pragma unroll
-    for (int k = 0; k < kNnzPerLane; k++) nfl += w[k] >> 15;
-    uint32_t incl = nfl;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(FULL, incl, d);
-        if (lane >= (uint32_t)d) incl += t;
+// Slice geometry of a tile from its 32-entry table (lane c holds cnt_ge[c], see TileDesc):
+// first step of tile-relative slice i, and the balancing weight (steps + one unit per slice).
+__device__ __forceinline__ uint32_t steps_before(uint32_t cnt, uint32_t i) {
+    return __reduce_add_sync(0xFFFFFFFFu, min(i, cnt));
+}
+__device__ __forceinline__ uint32_t steps_of(uint32_t cnt, uint32_t i) {
+    return __popc(__ballot_sync(0xFFFFFFFFu, cnt > i));
+}
+// tile-relative slice that contains step t: the largest i with S(i) <= t  (0 <= i < n_slices)
+__device__ __forceinline__ uint32_t slice_of_step(uint32_t cnt, uint32_t n_slices, uint32_t t) {
+    uint32_t lo = 0, hi = n_slices;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (steps_before(cnt, mid) <= t) lo = mid; else hi = mid;
     }
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    uint32_t seg = r.desc.x + incl - nfl;             // segment the lane's first flag closes
-    const uint32_t first_seg = seg;
+    return lo;
+}
 
-    // lane-local multiply-accumulate; segments that start AND end inside the lane are emitted at once
-    acc_t run = A::zero(), head = A::zero();
-    bool seen = false;
+// One warp streams tile-relative steps [ta, tb): a flat, contiguous run of (512 B values + 256 B
+// columns) steps that may start and end inside a slice. Lanes own lane streams; whenever a slice
+// (or the run) ends, the lane's partial sum is added to its row and the accumulator restarts.
+template <class A>
+__device__ __forceinline__ void stream_steps(const SpmvParams &p, const uint32_t *xs, uint64_t *bar, uint32_t parity,
+                                             uint32_t cnt, uint32_t slice_begin, uint32_t n_slices,
+                                             uint32_t step_begin, uint32_t ta, uint32_t tb, uint32_t lane) {
+    uint32_t remaining = tb - ta;
+    const size_t base = (size_t)(step_begin + ta) * kStepElems;
+    const uint4 *vp = reinterpret_cast<const uint4 *>(p.vals + base) + lane;
+    const uint2 *cp = reinterpret_cast<const uint2 *>(p.cols + base) + lane;
+
+    // the matrix stream does not depend on x: fill the ring before waiting for the x tile
+    uint4 vb[kPrefetch];
+    uint2 cb[kPrefetch];
 #pragma unroll
-    for (int k = 0; k < kNnzPerLane; k++) {
-        run = A::mac(run, v[k], xv[k]);
-        if (w[k] & kSegEndFlag) {
-            if (!seen) {
-                head = run;
-                seen = true;
-            } else {
-                A::emit(p.acc, __ldg(p.seg_row + seg), run);
-            }
-            seg++;
-            run = A::zero();
+    for (int j = 0; j < kPrefetch; j++)
+        if ((uint32_t)j < remaining) {
+            vb[j] = ldg_stream128(vp + j * kLanes);
+            cb[j] = ldg_stream64(cp + j * kLanes);
         }
+    vp += kPrefetch * kLanes;
+    cp += kPrefetch * kLanes;
+
+    uint32_t sl = 0, left = 0, row = 0, row_next = 0;
+    const uint32_t *rp = p.slice_rows;
+    if (remaining) {
+        sl = slice_of_step(cnt, n_slices, ta);
+        left = steps_before(cnt, sl + 1) - ta;                // steps of slice sl still ahead of us
+        rp = p.slice_rows + (size_t)(slice_begin + sl) * kLanes + lane;
+        row = __ldg(rp);
+        if (sl + 1 < n_slices) row_next = __ldg(rp + kLanes);
     }
 
-    // warp segmented scan of the open tails: I(l) = sum of tails from the nearest flagged lane
-    // at or below l (or lane 0) up to l
-    const uint32_t fmask = __ballot_sync(FULL, seen);
-    const uint32_t below = fmask & (FULL >> (31 - lane));
-    const uint32_t dist = below ? lane - (31 - __clz(below)) : lane;
-    acc_t I = run;
+    mbar_wait(bar, parity);
+    if (!remaining) return;
+
+    A acc;
+    acc.clear();
+    // Row update of a finished slice. Streams of one row sit in adjacent lanes (stable sort), and
+    // the pieces of a long row fill whole slices: then one warp reduction + one atomic replaces 32
+    // same-address atomics (which the L2 would serialise).
+    auto flush = [&]() {
+        typename A::acc_t v = acc.total();
+        if (__all_sync(0xFFFFFFFFu, row == __shfl_sync(0xFFFFFFFFu, row, 0))) {
+            v = A::warp_sum(v);
+            if (lane == 0) A::emit(p.acc, row, v);
+        } else {
+            A::emit(p.acc, row, v);
+        }
+    };
+    auto step_done = [&]() {
+        if (--left == 0) {                                   // warp-uniform: the slice is complete
+            flush();
+            acc.clear();
+            sl++;
+            rp += kLanes;
+            row = row_next;
+            if (sl + 1 < n_slices) row_next = __ldg(rp + kLanes);
+            if (sl + 8 < n_slices && lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 8 * kLanes));
+            left = steps_of(cnt, sl);
+        }
+    };
+    while (remaining >= (uint32_t)kPrefetch) {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        acc_t t = __shfl_up_sync(FULL, I, d);
-        if (dist >= (uint32_t)d) I = A::add(t, I);
+        for (int j = 0; j < kPrefetch; j++) {
+            mac4(acc, xs, vb[j], cb[j]);
+            if (remaining > (uint32_t)(kPrefetch + j)) {     // step (consumed + kPrefetch + j) exists
+                vb[j] = ldg_stream128(vp + j * kLanes);
+                cb[j] = ldg_stream64(cp + j * kLanes);
+            }
+            step_done();
+        }
+        vp += kPrefetch * kLanes;
+        cp += kPrefetch * kLanes;
+        remaining -= kPrefetch;
     }
-    acc_t carry = __shfl_up_sync(FULL, I, 1);
-    if (lane == 0) carry = A::zero();
-    if (seen) A::emit(p.acc, __ldg(p.seg_row + first_seg), A::add(carry, head));
-    // what is left open at the end of the chunk belongs to the next chunk's first segment
-    if (lane == 31 && (r.desc.y & kChunkContinues)) A::emit(p.acc, __ldg(p.seg_row + r.desc.x + total), I);
+#pragma unroll
+    for (int j = 0; j < kPrefetch - 1; j++)
+        if ((uint32_t)j < remaining) {
+            mac4(acc, xs, vb[j], cb[j]);
+            step_done();
+        }
+    // the run ended inside a slice: hand over what has been accumulated so far
+    if (left != steps_of(cnt, sl) && sl < n_slices) flush();
 }
 
 template <class A>
@@ -160,84 +224,93 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_tiles_kernel(const SpmvParam
     __shared__ __align__(8) uint64_t bar;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t n = p.chunk_end - p.chunk_begin;
-    const uint32_t c0 = p.chunk_begin + (uint32_t)(((unsigned long long)n * blockIdx.x) / gridDim.x);
-    const uint32_t c1 = p.chunk_begin + (uint32_t)(((unsigned long long)n * (blockIdx.x + 1)) / gridDim.x);
-    if (c0 >= c1) return;
+    const uint32_t g0 = __ldg(p.cta_seg + blockIdx.x), g1 = __ldg(p.cta_seg + blockIdx.x + 1);
+    const long long t_start = clock64();
 
-    if (tid == 0) mbar_init(&bar, 1);
-    __syncthreads();
+    // Drain the previous launch's accumulators (clamp / copy into y, re-zero): the pe dump + result
+    // drain of the reference (pe.h:95-116, spmv_result_drain.cpp) and the PE's reset loop
+    // (pe.h:131-135). The kernel boundary is the barrier that makes those sums final, and this
+    // launch accumulates into the other buffer, so the drain overlaps the x staging below.
+    auto drain = [&]() {
+        if (p.drain_acc) {
+            for (uint32_t r = p.drain_begin + blockIdx.x * kThreads + tid; r < p.drain_end; r += gridDim.x * kThreads)
+                p.y[r] = A::drain(p.drain_acc, r);
+            if (blockIdx.x == 0 && tid == 0) (void)A::drain(p.drain_acc, p.trash_row);
+        }
+    };
 
-    uint32_t parity = 0;
-    uint32_t c = c0;
-    uint32_t tile = __ldg(&p.chunks[c0].tile) & ~kChunkContinues;
-    while (c < c1) {
-        const TileDesc td = p.tiles[tile];
-        if (td.chunk_end <= c) { tile++; continue; }          // empty tile
-        const uint32_t sub_end = min(c1, td.chunk_end);
-
-        // stage the x tile: the vector loader + vecbuf writer of the reference
+    if (g0 < g1) {
         if (tid == 0) {
-            fence_proxy_async();
-            const uint32_t bytes = td.col_count * 4u;
-            mbar_arrive_expect_tx(&bar, bytes);
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(p.x + td.col_base);
-            for (uint32_t off = 0; off < bytes; off += kBulkPiece)
-                bulk_g2s(smem_raw + off, src + off, min(kBulkPiece, bytes - off), &bar);
+            mbar_init(&bar, 1);
+            xs[kPadCol] = 0u;                                     // what padding slots multiply by
         }
-
-        // the matrix stream does not depend on x: issue the first loads before waiting for the tile
-        uint32_t ch = c + warp;
-        ChunkRegs cur;
-        if (ch < sub_end) load_chunk(p, ch, lane, cur);
-        mbar_wait(&bar, parity);
-        parity ^= 1u;
-        while (ch < sub_end) {
-            const uint32_t nx = ch + kWarps;
-            ChunkRegs nxt;
-            if (nx < sub_end) load_chunk(p, nx, lane, nxt);
-            process_chunk<A>(p, xs, cur, lane);
-            cur = nxt;
-            ch = nx;
+        __syncthreads();
+        uint32_t parity = 0;
+        for (uint32_t g = g0; g < g1; g++) {
+            const uint4 sg = __ldg(reinterpret_cast<const uint4 *>(p.segs + g));   // tile, t_lo, t_hi
+            const TileDesc *td = p.tiles + sg.x;
+            const uint32_t cnt = __ldg(&td->cnt_ge[lane]);
+            const uint32_t slice_begin = __ldg(&td->slice_begin);
+            const uint32_t n_slices = __ldg(&td->slice_end) - slice_begin;
+            // stage the x tile: the vector loader + vecbuf writer of the reference
+            if (tid == 0) {
+                fence_proxy_async();
+                const uint32_t bytes = __ldg(&td->col_count) * 4u;
+                mbar_arrive_expect_tx(&bar, bytes);
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(p.x + __ldg(&td->col_base));
+                for (uint32_t off = 0; off < bytes; off += kBulkPiece)
+                    bulk_g2s(smem_raw + off, src + off, min(kBulkPiece, bytes - off), &bar);
+            }
+            if (g == g0) drain();
+            // equal shares of the segment's steps for the warps
+            const uint32_t n = sg.z - sg.y;
+            const uint32_t ta = sg.y + (uint32_t)(((unsigned long long)n * warp) / kWarps);
+            const uint32_t tb = sg.y + (uint32_t)(((unsigned long long)n * (warp + 1)) / kWarps);
+            stream_steps<A>(p, xs, &bar, parity, cnt, slice_begin, n_slices, __ldg(&td->step_begin), ta, tb, lane);
+            parity ^= 1u;
+            if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * (kWarps + 2) + warp] = clock64() - t_start;
+            __syncthreads();                                       // everyone is done with this x tile
         }
-        c = sub_end;
-        tile++;
-        __syncthreads();                                       // everyone is done with this x tile
+    } else {
+        drain();
     }
+    if (p.trace && tid == 0) p.trace[(size_t)blockIdx.x * (kWarps + 2) + kWarps] = clock64() - t_start;
 }
 
-__global__ void finalize_fixed_kernel(const unsigned long long *__restrict__ acc, uint32_t *__restrict__ y,
-                                      uint32_t row_begin, uint32_t row_end) {
-    uint32_t r = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < row_end) {
-        unsigned long long a = acc[r];
-        y[r] = (a >> 32) ? 0xFFFFFFFFu : (uint32_t)a;          // AP_SAT of the accumulator (pe.h:72)
-    }
+template <class A>
+__global__ void drain_kernel(void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end, uint32_t trash_row) {
+    for (uint32_t r = row_begin + blockIdx.x * blockDim.x + threadIdx.x; r < row_end; r += gridDim.x * blockDim.x)
+        y[r] = A::drain(acc, r);
+    if (blockIdx.x == 0 && threadIdx.x == 0) (void)A::drain(acc, trash_row);
 }
 
 }  // namespace
 
 cudaError_t configure_kernels() {
     cudaError_t e = cudaFuncSetAttribute(spmv_tiles_kernel<FixedArith>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kXTileBytes);
+                                         (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(spmv_tiles_kernel<FloatArith>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)kXTileBytes);
+                                (int)kSmemBytes);
 }
 
-void launch_spmv_tiles(int arith, const SpmvParams &p, int grid, cudaStream_t stream) {
-    if (p.chunk_end <= p.chunk_begin) return;
+cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, cudaStream_t stream) {
     if (arith == kArithFixed)
-        spmv_tiles_kernel<FixedArith><<<grid, kThreads, kXTileBytes, stream>>>(p);
+        spmv_tiles_kernel<FixedArith><<<grid, kThreads, kSmemBytes, stream>>>(p);
     else
-        spmv_tiles_kernel<FloatArith><<<grid, kThreads, kXTileBytes, stream>>>(p);
+        spmv_tiles_kernel<FloatArith><<<grid, kThreads, kSmemBytes, stream>>>(p);
+    return cudaGetLastError();
 }
 
-void launch_finalize_fixed(const unsigned long long *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end,
-                           cudaStream_t stream) {
-    if (row_end <= row_begin) return;
-    uint32_t n = row_end - row_begin;
-    finalize_fixed_kernel<<<(n + 255) / 256, 256, 0, stream>>>(acc, y, row_begin, row_end);
+cudaError_t launch_drain(int arith, void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end,
+                         uint32_t trash_row, cudaStream_t stream) {
+    const uint32_t n = row_end > row_begin ? row_end - row_begin : 1;
+    const int grid = (int)std::min<uint32_t>((n + 255) / 256, 148u * 8u);
+    if (arith == kArithFixed)
+        drain_kernel<FixedArith><<<grid, 256, 0, stream>>>(acc, y, row_begin, row_end, trash_row);
+    else
+        drain_kernel<FloatArith><<<grid, 256, 0, stream>>>(acc, y, row_begin, row_end, trash_row);
+    return cudaGetLastError();
 }
 
 }  // namespace hsb

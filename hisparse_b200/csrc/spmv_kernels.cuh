@@ -1,28 +1,34 @@
-// sm_100a SpMV kernels over the tile-stream format (tile_format.h).
+// sm_100a SpMV kernel over the tile-stream format (tile_format.h).
 //
 // One persistent CTA per SM replaces one HiSparse "cluster" pipeline
-// (spmv/libfpga/spmv_cluster.h:196-373):
+// (spmv/libfpga/spmv_cluster.h:196-373); a whole SpMV (all row partitions or one) is ONE launch:
 //
 //   reference unit (file:line)                          here
 //   ------------------------------------------------    --------------------------------------------
 //   spmv_vector_loader + axis_duplicate + vecbuf_writer x tile -> shared memory with cp.async.bulk
 //     (spmv_vector_loader.cpp:7-79, stream_utils.h:8,     (TMA bulk copy, mbarrier complete_tx);
-//      vecbuf_access_unit.h:92-136)                       one 128 KB tile = LOGICAL_VB_SIZE words
-//   CPSR_matrix_loader (spmv_cluster.h:34-107)          128-bit ld.global.nc streaming loads, each
-//                                                         warp-wide load one contiguous 512 B
+//      vecbuf_access_unit.h:92-136)                       one <=128 KB tile = LOGICAL_VB_SIZE words
+//   CPSR_matrix_loader (spmv_cluster.h:34-107)          every warp streams ONE contiguous run of slice steps
+//                                                         with 128-bit / 64-bit ld.global.nc loads (each
+//                                                         warp-wide load a contiguous 512 / 256 B), a
+//                                                         register ring keeps kPrefetch steps in flight
+//                                                         across slice boundaries
 //   shuffler<EDGE> + vecbuf_reader                      per-lane shared-memory gather xs[col]
 //     (shuffle.h:380-468, vecbuf_access_unit.h:18-84)     (bank = col % 32, conflicts replayed by HW)
-//   shuffler<UPDATE> + pe (shuffle.h, pe.h:22-90)       register accumulation per lane + warp
-//                                                         segmented scan keyed by end-of-segment flags
-//   pe dump + result_packer + axis_merge + result_drain one red.global.add per (row, tile) segment
-//     (pe.h:95-116, spmv_cluster.h:133-193,                into the row accumulator, then a clamp pass
-//      stream_utils.h:36-75, spmv_result_drain.cpp)
+//   shuffler<UPDATE> + pe (shuffle.h, pe.h:22-90)       every lane owns a whole lane stream (a row
+//                                                         segment) and accumulates it in registers: no
+//                                                         routing by row, no read-after-write hazard
+//   pe dump + result_packer + axis_merge + result_drain one red.global.add per lane stream (or per warp when
+//     (pe.h:95-116, spmv_cluster.h:133-193,                a slice holds one row) into the row accumulator;
+//      stream_utils.h:36-75, spmv_result_drain.cpp)        the accumulators are double buffered and drained
+//                                                         (clamp, store y, re-zero) in the prologue of the
+//                                                         next launch or by a drain kernel at sync time
 //
 // Arithmetic:
 //   fixed  : VAL_T = ap_ufixed<32,8,AP_RND,AP_SAT> (spmv/libfpga/common.h:38). product =
 //            min((a*b + 2^23) >> 24, 2^32-1) (pe.h:64), accumulation saturating (pe.h:72). All terms
 //            are >= 0 and the clamp is at a constant, so y = min(sum of products, 2^32-1) in ANY
-//            order: we add the clamped products exactly in 64 bits and clamp once at the end.
+//            order: products are summed exactly (64-bit) and clamped once in the drain.
 //   float  : fp32 multiply then fp32 add, not fused (pe-pob.h:64-66, pe-stall.h:53,138).
 #ifndef HISPARSE_B200_SPMV_KERNELS_CUH_
 #define HISPARSE_B200_SPMV_KERNELS_CUH_
@@ -36,24 +42,33 @@ namespace hsb {
 constexpr int kThreads = 1024;                       // 32 warps: one CTA per SM
 constexpr int kWarps = kThreads / 32;
 constexpr uint32_t kXTileBytes = kMaxTileCols * 4;   // 128 KB
+constexpr uint32_t kSmemBytes = kXTileBytes + 16;    // + the constant-zero word padding slots gather
 constexpr uint32_t kBulkPiece = 16384;               // bytes per cp.async.bulk
+constexpr int kPrefetch = 4;                         // slice steps in flight per warp
 
 struct SpmvParams {
     const uint32_t *vals;
-    const uint16_t *cidx;
-    const ChunkDesc *chunks;
+    const uint16_t *cols;
+    const uint32_t *slice_rows;
     const TileDesc *tiles;
-    const uint32_t *seg_row;
+    const uint32_t *cta_seg;      // gridDim.x + 1 : CTA b runs segs[cta_seg[b] .. cta_seg[b+1])
+    const Segment *segs;          // (tile, [t_lo, t_hi) tile-relative steps): one x staging each
     const uint32_t *x;            // packed dense vector, raw 32-bit words
-    void *acc;                    // fixed: uint64 per row; float: the fp32 result itself
-    uint32_t chunk_begin, chunk_end;
+    void *acc;                    // row accumulators of THIS launch (uint64 fixed / fp32 float), rows + 1 entries,
+                                  // all zero on entry
+    void *drain_acc;              // accumulators of the PREVIOUS launch still to be drained into y, or null
+    uint32_t *y;                  // packed result, raw 32-bit words
+    uint32_t drain_begin, drain_end;  // rows of drain_acc to drain
+    uint32_t trash_row;           // accumulator index of unused lanes (== rows)
+    unsigned long long *trace;    // optional [gridDim.x][kWarps + 2] SM-clock stamps (profiling aid), or null
 };
 
 enum { kArithFixed = 0, kArithFloat = 1 };
 
-void launch_spmv_tiles(int arith, const SpmvParams &p, int grid, cudaStream_t stream);
-void launch_finalize_fixed(const unsigned long long *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end,
-                           cudaStream_t stream);
+cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, cudaStream_t stream);
+// drain only: y[r] = clamp(acc[r]), acc[r] = 0 for r in [row_begin, row_end) and the trash slot
+cudaError_t launch_drain(int arith, void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end,
+                         uint32_t trash_row, cudaStream_t stream);
 cudaError_t configure_kernels();
 
 }  // namespace hsb

@@ -1,12 +1,20 @@
 // Host-side builder for the tile-stream format (see tile_format.h). This is the B200
 // counterpart of the reference's CSR -> CPSR preprocessing (sw/data_formatter.h:468-544):
 // same inputs (a CSR with 32-bit indices and 32-bit value words, a row-partition length, a
-// column-partition length), different output layout. Two passes (count, then place), both
-// parallel over nnz-balanced row slices, so preprocessing is not the single-threaded
-// bottleneck it is in the reference (paper Table 8: 0.02 - 10.6 s).
+// column-partition length), different output layout. All passes are parallel (row slabs, tiles,
+// slices), so preprocessing is not the single-threaded bottleneck it is in the reference
+// (paper Table 8: 0.02 - 10.6 s).
+//
+//   stage A  column partitioning: per (row partition, column tile) the non-zeros in CSR order
+//            with column ids rebased to the tile           (== util_convert_csr_to_dds, :256-313)
+//   stage B  per tile: cut row segments into lane streams of <= kMaxStreamLen, sort the streams
+//            by length (descending, stable), group 32 per slice  (replaces util_pack_rows'
+//            cyclic row->lane assignment, :407-443, by a length-sorted one)
+//   stage C  copy every stream into its slice in the warp-coalesced element order
 #include "tile_format.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <thread>
 
@@ -22,8 +30,13 @@ uint32_t choose_tile_cols(uint32_t cols) {
 
 namespace {
 
-struct Slice {
+struct Slab {
     uint32_t part, r0, r1;       // rows [r0, r1) of row partition `part`
+};
+struct Stream {
+    uint32_t row;
+    uint32_t len;
+    uint64_t src;                // position of its first non-zero in the stage-A arrays
 };
 
 template <class F> void parallel_for(size_t n, int n_threads, F f) {
@@ -33,10 +46,15 @@ template <class F> void parallel_for(size_t n, int n_threads, F f) {
     }
     std::vector<std::thread> th;
     size_t nt = std::min<size_t>(n_threads, n);
+    std::atomic<size_t> next(0);
     for (size_t t = 0; t < nt; t++)
-        th.emplace_back([&, t]() { for (size_t i = t; i < n; i += nt) f(i); });
+        th.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < n;) f(i); });
     for (auto &x : th) x.join();
 }
+
+// number of lane streams a segment of n non-zeros is cut into, and the length of piece q
+inline uint32_t n_pieces(uint32_t n) { return (n + kMaxStreamLen - 1) / kMaxStreamLen; }
+inline uint32_t piece_len(uint32_t n, uint32_t pieces, uint32_t q) { return n / pieces + (q < n % pieces ? 1u : 0u); }
 
 }  // namespace
 
@@ -49,7 +67,7 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
     for (uint32_t r = 0; r < rows; r++)
         if (indptr[r + 1] < indptr[r]) return fail("indptr is not monotone");
     const uint64_t nnz = rows ? indptr[rows] : 0;
-    if (n_threads <= 0) n_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (n_threads <= 0) n_threads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
     if (nnz < (1u << 16)) n_threads = 1;
 
     TiledMatrix &M = *out;
@@ -60,10 +78,11 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
     M.tile_cols = tile_cols;
     M.n_col_tiles = std::max(1u, (cols + tile_cols - 1) / tile_cols);
     const uint32_t T = M.n_col_tiles;
+    const size_t NT = (size_t)M.n_row_parts * T;
 
-    // nnz-balanced row slices inside every row partition
-    std::vector<Slice> slices;
-    std::vector<uint32_t> part_slice_begin(M.n_row_parts + 1, 0);
+    // ---- stage A -------------------------------------------------------------------------
+    std::vector<Slab> slabs;
+    std::vector<uint32_t> part_slab_begin(M.n_row_parts + 1, 0);
     for (uint32_t j = 0; j < M.n_row_parts; j++) {
         uint32_t r0 = j * M.rows_per_part, r1 = (uint32_t)std::min<uint64_t>(rows, (uint64_t)r0 + M.rows_per_part);
         uint64_t e0 = indptr[r0], e1 = indptr[r1];
@@ -76,18 +95,17 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
                 cut = (uint32_t)(std::lower_bound(indptr + prev, indptr + r1, (uint32_t)target) - indptr);
                 cut = std::min(std::max(cut, prev), r1);
             }
-            if (cut > prev || s == ns) slices.push_back(Slice{j, prev, cut});
+            if (cut > prev || s == ns) slabs.push_back(Slab{j, prev, cut});
             prev = cut;
         }
-        part_slice_begin[j + 1] = (uint32_t)slices.size();
+        part_slab_begin[j + 1] = (uint32_t)slabs.size();
     }
-    const size_t NS = slices.size();
+    const size_t NS = slabs.size();
 
-    // pass 1: per (slice, tile) non-zero and segment counts
     std::vector<uint64_t> cnt(NS * T, 0), seg(NS * T, 0);
-    bool bad_col = false;
+    std::atomic<bool> bad_col(false);
     parallel_for(NS, n_threads, [&](size_t s) {
-        const Slice &sl = slices[s];
+        const Slab &sl = slabs[s];
         std::vector<uint32_t> stamp(T, 0xFFFFFFFFu);
         uint64_t *c = &cnt[s * T], *g = &seg[s * T];
         for (uint32_t r = sl.r0; r < sl.r1; r++)
@@ -101,87 +119,247 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
     });
     if (bad_col) return fail("column index out of range");
 
-    // layout: tiles in (row partition, column tile) order; chunks and segments numbered globally
-    M.tiles.resize((size_t)M.n_row_parts * T);
-    M.part_chunk_begin.assign(M.n_row_parts + 1, 0);
-    std::vector<uint64_t> pos0(NS * T), seg0(NS * T);   // first stream position / segment of a slice in a tile
-    uint64_t chunk_cursor = 0, seg_cursor = 0;
-    for (uint32_t j = 0; j < M.n_row_parts; j++) {
-        M.part_chunk_begin[j] = (uint32_t)chunk_cursor;
-        for (uint32_t t = 0; t < T; t++) {
-            uint64_t n = 0;
-            for (uint32_t s = part_slice_begin[j]; s < part_slice_begin[j + 1]; s++) {
-                pos0[(size_t)s * T + t] = chunk_cursor * kChunkNnz + n;
-                seg0[(size_t)s * T + t] = seg_cursor;
-                n += cnt[(size_t)s * T + t];
-                seg_cursor += seg[(size_t)s * T + t];
+    std::vector<uint64_t> tile_nnz0(NT + 1, 0), tile_seg0(NT + 1, 0);
+    std::vector<uint64_t> pos0(NS * T), seg0(NS * T);
+    {
+        uint64_t p = 0, g = 0;
+        for (uint32_t j = 0; j < M.n_row_parts; j++)
+            for (uint32_t t = 0; t < T; t++) {
+                tile_nnz0[(size_t)j * T + t] = p;
+                tile_seg0[(size_t)j * T + t] = g;
+                for (uint32_t s = part_slab_begin[j]; s < part_slab_begin[j + 1]; s++) {
+                    pos0[(size_t)s * T + t] = p; seg0[(size_t)s * T + t] = g;
+                    p += cnt[(size_t)s * T + t]; g += seg[(size_t)s * T + t];
+                }
             }
-            TileDesc &td = M.tiles[(size_t)j * T + t];
-            std::memset(&td, 0, sizeof(td));
-            td.col_base = t * tile_cols;
-            uint32_t width = std::min(tile_cols, cols > td.col_base ? cols - td.col_base : 0u);
-            td.col_count = (width + 7u) & ~7u;
-            td.row_part = j;
-            td.chunk_begin = (uint32_t)chunk_cursor;
-            chunk_cursor += (n + kChunkNnz - 1) / kChunkNnz;
-            td.chunk_end = (uint32_t)chunk_cursor;
-        }
+        tile_nnz0[NT] = p; tile_seg0[NT] = g;
     }
-    M.part_chunk_begin[M.n_row_parts] = (uint32_t)chunk_cursor;
-    if (chunk_cursor >= (1ull << 31) || seg_cursor >= (1ull << 32)) return fail("matrix too large for 32-bit chunk/segment ids");
-    const size_t NC = (size_t)chunk_cursor;
-    M.vals.assign(NC * kChunkNnz, 0u);
-    M.cidx.assign(NC * kChunkNnz, (uint16_t)0);
-    M.seg_row.assign((size_t)seg_cursor, 0u);
-    M.chunks.assign(NC, ChunkDesc{0, 0});
-
-    // pass 2: place every non-zero; flag the last one of each (row, tile) segment
+    std::vector<uint32_t> a_vals(nnz), a_seg_row(tile_seg0[NT]), a_seg_len(tile_seg0[NT]);
+    std::vector<uint16_t> a_cols(nnz);
     parallel_for(NS, n_threads, [&](size_t s) {
-        const Slice &sl = slices[s];
+        const Slab &sl = slabs[s];
         std::vector<uint64_t> cur(pos0.begin() + s * T, pos0.begin() + (s + 1) * T);
         std::vector<uint64_t> scur(seg0.begin() + s * T, seg0.begin() + (s + 1) * T);
-        std::vector<uint64_t> last(T, ~0ull);
+        std::vector<uint32_t> in_row(T, 0);
         std::vector<uint32_t> touched;
         for (uint32_t r = sl.r0; r < sl.r1; r++) {
             for (uint32_t e = indptr[r]; e < indptr[r + 1]; e++) {
                 uint32_t col = indices[e], t = col / tile_cols;
                 uint64_t p = cur[t]++;
-                size_t chunk = (size_t)(p / kChunkNnz);
-                int j = (int)(p % kChunkNnz);
-                M.vals[chunk * kChunkNnz + val_slot(j / kNnzPerLane, j % kNnzPerLane)] = vals[e];
-                M.cidx[p] = (uint16_t)(col - t * tile_cols);
-                if (last[t] == ~0ull) touched.push_back(t);
-                last[t] = p;
+                a_vals[p] = vals[e];
+                a_cols[p] = (uint16_t)(col - t * tile_cols);
+                if (in_row[t]++ == 0) touched.push_back(t);
             }
             for (uint32_t t : touched) {
-                M.cidx[last[t]] |= kSegEndFlag;
-                M.seg_row[scur[t]++] = r;
-                last[t] = ~0ull;
+                a_seg_row[scur[t]] = r;
+                a_seg_len[scur[t]] = in_row[t];
+                scur[t]++;
+                in_row[t] = 0;
             }
             touched.clear();
         }
     });
 
-    // chunk descriptors: running segment count + "stream continues past the last flag"
-    std::vector<uint32_t> flags_in(NC, 0);
-    parallel_for((size_t)M.tiles.size(), n_threads, [&](size_t ti) {
-        const TileDesc &td = M.tiles[ti];
-        for (uint32_t c = td.chunk_begin; c < td.chunk_end; c++) {
-            const uint16_t *w = &M.cidx[(size_t)c * kChunkNnz];
-            uint32_t n = 0;
-            int last_flag = -1;
-            for (int j = 0; j < kChunkNnz; j++)
-                if (w[j] & kSegEndFlag) { n++; last_flag = j; }
-            flags_in[c] = n;
-            // every tile stream ends with a flagged non-zero, so real entries after the last flag
-            // exist exactly when the chunk is not the tile's last one or ... it simply has them:
-            bool cont = (c + 1 < td.chunk_end) && last_flag != kChunkNnz - 1;
-            M.chunks[c].tile = (uint32_t)ti | (cont ? kChunkContinues : 0u);
+    // ---- stage B -------------------------------------------------------------------------
+    std::vector<uint64_t> t_streams(NT + 1, 0), t_slices(NT + 1, 0), t_steps(NT + 1, 0);
+    auto tile_plan = [&](size_t ti, uint32_t *hist /*[kMaxStreamLen+1]*/) {
+        std::fill(hist, hist + kMaxStreamLen + 1, 0u);
+        for (uint64_t g = tile_seg0[ti]; g < tile_seg0[ti + 1]; g++) {
+            uint32_t n = a_seg_len[g], p = n_pieces(n);
+            hist[n / p] += p - n % p;
+            if (n % p) hist[n / p + 1] += n % p;
+        }
+    };
+    parallel_for(NT, n_threads, [&](size_t ti) {
+        uint32_t hist[kMaxStreamLen + 1];
+        tile_plan(ti, hist);
+        uint64_t ns = 0, steps = 0, slices = 0;
+        // walk lengths in descending order, 32 streams per slice; a slice is as long as its first stream
+        uint64_t idx = 0;
+        for (uint32_t len = kMaxStreamLen; len >= 1; len--) {
+            uint64_t h = hist[len];
+            if (!h) continue;
+            // slices that START inside this length class
+            uint64_t first_start = (idx + kLanes - 1) / kLanes * kLanes;       // next slice boundary >= idx
+            if (first_start < idx + h) {
+                uint64_t n_start = (idx + h - first_start + kLanes - 1) / kLanes;
+                slices += n_start;
+                steps += n_start * ((len + kSlotBlock - 1) / kSlotBlock);
+            }
+            idx += h;
+            ns += h;
+        }
+        t_streams[ti + 1] = ns; t_slices[ti + 1] = slices; t_steps[ti + 1] = steps;
+    });
+    for (size_t ti = 0; ti < NT; ti++) {
+        t_streams[ti + 1] += t_streams[ti]; t_slices[ti + 1] += t_slices[ti]; t_steps[ti + 1] += t_steps[ti];
+    }
+    if (t_slices[NT] >= (1ull << 31) || t_steps[NT] >= (1ull << 32) || NT >= (1ull << 24))
+        return fail("matrix too large for 32-bit slice / step ids");
+    M.n_streams = t_streams[NT];
+    const size_t NSL = (size_t)t_slices[NT];
+    M.slices.assign(NSL, SliceDesc{0, 0});
+    M.slice_rows.assign(NSL * kLanes, rows);
+    M.vals.assign((size_t)t_steps[NT] * kStepElems, 0u);
+    M.cols16.assign((size_t)t_steps[NT] * kStepElems, kPadCol);
+    M.tiles.resize(NT);
+    M.part_slice_begin.assign(M.n_row_parts + 1, 0);
+    std::vector<Stream> streams((size_t)t_streams[NT]);
+
+    parallel_for(NT, n_threads, [&](size_t ti) {
+        uint32_t hist[kMaxStreamLen + 1];
+        tile_plan(ti, hist);
+        // descending counting sort: first output index of every length class
+        uint64_t start[kMaxStreamLen + 2];
+        uint64_t run = t_streams[ti];
+        for (uint32_t len = kMaxStreamLen; len >= 1; len--) { start[len] = run; run += hist[len]; }
+        uint64_t src = tile_nnz0[ti];
+        for (uint64_t g = tile_seg0[ti]; g < tile_seg0[ti + 1]; g++) {
+            uint32_t n = a_seg_len[g], p = n_pieces(n);
+            for (uint32_t q = 0; q < p; q++) {
+                uint32_t l = piece_len(n, p, q);
+                streams[start[l]++] = Stream{a_seg_row[g], l, src};
+                src += l;
+            }
+        }
+        TileDesc &td = M.tiles[ti];
+        std::memset(&td, 0, sizeof td);
+        uint32_t t = (uint32_t)(ti % T);
+        td.col_base = t * tile_cols;
+        uint32_t width = std::min(tile_cols, cols > td.col_base ? cols - td.col_base : 0u);
+        td.col_count = (width + 7u) & ~7u;
+        td.row_part = (uint32_t)(ti / T);
+        td.slice_begin = (uint32_t)t_slices[ti];
+        td.slice_end = (uint32_t)t_slices[ti + 1];
+        td.step_begin = (uint32_t)t_steps[ti];
+        uint64_t off = t_steps[ti];
+        for (uint64_t s = t_slices[ti], i = t_streams[ti]; s < t_slices[ti + 1]; s++, i += kLanes) {
+            uint32_t steps = (streams[i].len + kSlotBlock - 1) / kSlotBlock;
+            M.slices[s].off = (uint32_t)off;
+            M.slices[s].tile_steps = ((uint32_t)ti << 8) | steps;
+            off += steps;
+            for (uint32_t c = 0; c < steps; c++) td.cnt_ge[c]++;
         }
     });
-    uint32_t run = 0;
-    for (size_t c = 0; c < NC; c++) { M.chunks[c].seg_base = run; run += flags_in[c]; }
+    for (uint32_t j = 0; j <= M.n_row_parts; j++) M.part_slice_begin[j] = (uint32_t)t_slices[(size_t)j * T];
+
+    // ---- stage C -------------------------------------------------------------------------
+    const size_t kBlock = 256;                               // slices per task
+    parallel_for((NSL + kBlock - 1) / kBlock, n_threads, [&](size_t blk) {
+        for (size_t s = blk * kBlock; s < std::min(NSL, (blk + 1) * kBlock); s++) {
+            const size_t ti = M.slices[s].tile_steps >> 8;
+            const uint64_t i0 = t_streams[ti] + (s - t_slices[ti]) * kLanes;
+            const size_t base = (size_t)M.slices[s].off * kStepElems;
+            for (int lane = 0; lane < kLanes; lane++) {
+                uint64_t i = i0 + lane;
+                if (i >= t_streams[ti + 1]) break;
+                const Stream &st = streams[i];
+                M.slice_rows[s * kLanes + lane] = st.row;
+                for (uint32_t k = 0; k < st.len; k++) {
+                    size_t e = slice_elem(base, lane, k);
+                    M.vals[e] = a_vals[st.src + k];
+                    M.cols16[e] = a_cols[st.src + k];
+                }
+            }
+        }
+    });
     return true;
+}
+
+namespace {
+// tile-relative step position at which the cost prefix (steps + slices started) of tile `td` reaches w
+uint32_t step_at_cost(const TiledMatrix &m, const TileDesc &td, double w) {
+    // cost prefix before slice i: S(i) + i ; inside slice i after k steps: S(i) + i + 1 + k
+    uint32_t lo = 0, hi = td.slice_end - td.slice_begin;       // find last slice whose start cost <= w
+    auto start_cost = [&](uint32_t i) {
+        return (double)(m.slices[td.slice_begin + i].off - td.step_begin) + i;
+    };
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) / 2;
+        if (start_cost(mid) <= w) lo = mid; else hi = mid;
+    }
+    const SliceDesc &sd = m.slices[td.slice_begin + lo];
+    uint32_t steps = sd.tile_steps & 0xFFu, s_before = sd.off - td.step_begin;
+    double inside = w - start_cost(lo) - 1.0;
+    uint32_t k = inside <= 0 ? 0u : (uint32_t)std::min<double>(steps, inside + 0.5);
+    return s_before + k;
+}
+uint32_t tile_steps_total(const TiledMatrix &m, const TileDesc &td) {
+    if (td.slice_end == td.slice_begin) return 0;
+    const SliceDesc &last = m.slices[td.slice_end - 1];
+    return last.off + (last.tile_steps & 0xFFu) - td.step_begin;
+}
+}  // namespace
+
+void plan_launch(const TiledMatrix &m, uint32_t tile_begin, uint32_t tile_end, uint32_t ctas,
+                 std::vector<uint32_t> *cta_seg, std::vector<Segment> *segs) {
+    cta_seg->assign(ctas + 1, (uint32_t)segs->size());
+    std::vector<uint32_t> live;
+    std::vector<double> cost;
+    double total = 0;
+    for (uint32_t t = tile_begin; t < tile_end; t++) {
+        const TileDesc &td = m.tiles[t];
+        if (td.slice_end == td.slice_begin) continue;
+        live.push_back(t);
+        cost.push_back((double)tile_steps_total(m, td) + (td.slice_end - td.slice_begin));
+        total += cost.back();
+    }
+    if (live.empty() || ctas == 0) return;
+    if (live.size() <= ctas) {
+        // whole CTAs per tile, proportional to cost (largest remainder, at least one each)
+        std::vector<uint32_t> n(live.size(), 1);
+        uint32_t used = (uint32_t)live.size();
+        std::vector<double> want(live.size());
+        for (size_t i = 0; i < live.size(); i++) want[i] = cost[i] / total * ctas;
+        while (used < ctas) {
+            size_t best = 0;
+            double gap = -1e300;
+            for (size_t i = 0; i < live.size(); i++)
+                if (want[i] - n[i] > gap) { gap = want[i] - n[i]; best = i; }
+            n[best]++;
+            used++;
+        }
+        uint32_t b = 0;
+        for (size_t i = 0; i < live.size(); i++) {
+            const TileDesc &td = m.tiles[live[i]];
+            const uint32_t steps = tile_steps_total(m, td);
+            uint32_t prev = 0;
+            for (uint32_t k = 1; k <= n[i]; k++) {
+                uint32_t cut = k == n[i] ? steps : std::max(prev, std::min(steps, step_at_cost(m, td, cost[i] * k / n[i])));
+                (*cta_seg)[b] = (uint32_t)segs->size();
+                if (cut > prev) segs->push_back(Segment{live[i], prev, cut, 0});
+                b++;
+                prev = cut;
+            }
+        }
+        for (; b <= ctas; b++) (*cta_seg)[b] = (uint32_t)segs->size();
+        return;
+    }
+    // more tiles than CTAs: contiguous equal-cost split of the tile sequence; a CTA runs whole
+    // tiles and at most a partial tile at either end
+    size_t i = 0;
+    uint32_t prev = 0;                 // next unassigned step of tile live[i]
+    double done = 0;                   // cost of everything before tile live[i]
+    for (uint32_t b = 0; b < ctas; b++) {
+        (*cta_seg)[b] = (uint32_t)segs->size();
+        const double target = total * (b + 1) / ctas;
+        while (i < live.size()) {
+            const TileDesc &td = m.tiles[live[i]];
+            const uint32_t steps = tile_steps_total(m, td);
+            if (b + 1 == ctas || done + cost[i] <= target) {            // the rest of this tile
+                if (steps > prev) segs->push_back(Segment{live[i], prev, steps, 0});
+                done += cost[i];
+                i++;
+                prev = 0;
+                continue;
+            }
+            uint32_t cut = std::max(prev, std::min(steps, step_at_cost(m, td, target - done)));
+            if (cut > prev) segs->push_back(Segment{live[i], prev, cut, 0});
+            prev = cut;
+            break;
+        }
+    }
+    (*cta_seg)[ctas] = (uint32_t)segs->size();
 }
 
 }  // namespace hsb

@@ -1,23 +1,27 @@
 // B200 tile-stream matrix format ("TS-CPSR") -- the HBM layout the sm_100a SpMV kernels read.
 //
 // It plays the role of the reference's CPSR channel images (sw/data_formatter.h:194-238,
-// sw/host.cpp:163-231) but is laid out for 32-wide warps and 128-byte coalescing instead of
-// 8-lane 64-byte HBM packets:
+// sw/host.cpp:163-231) and keeps CPSR's central idea -- every processing lane streams whole rows
+// (sw/data_formatter.h:407-443: row r goes to channel (r/8)%C, lane r%8) -- re-shaped for
+// 32-wide warps, 128-byte coalescing and a load-balanced persistent grid:
 //
 //   * rows are cut into row partitions (the reference's LOGICAL_OB_SIZE cut,
 //     sw/data_formatter.h:494), columns into tiles of <= 32768 columns (the reference's
 //     LOGICAL_VB_SIZE = 32768-word vector buffer, spmv/libfpga/common.h:165,179) so that the
-//     x tile of a work unit fits in one CTA's shared memory and a local column id fits 15 bits;
-//   * inside a (row partition, column tile) the non-zeros are kept in CSR order as one stream;
-//     the last non-zero of every (row, tile) segment carries an end-of-segment flag in bit 15
-//     of its 16-bit column word -- the in-band analogue of the reference's end-of-row marker
-//     (IDX_MARKER entries, sw/data_formatter.h:51-171) at zero extra bytes;
-//   * the stream is cut into chunks of 256 non-zeros = 32 lanes x 8 consecutive non-zeros;
-//     values are stored so that each of a warp's two 128-bit loads is one contiguous 512 B;
-//   * seg_row[s] is the matrix row of the s-th segment (the row the reference recovers by
-//     counting markers, spmv/libfpga/spmv_cluster.h:78-83).
+//     x tile of a work unit fits in one CTA's shared memory and a local column id fits 16 bits;
+//   * inside a (row partition, column tile) every non-empty row segment becomes one or more
+//     LANE STREAMS of at most kMaxStreamLen non-zeros (long rows are split so that no lane
+//     serialises a hub row -- the reference instead pads every lane to the longest,
+//     sw/host.cpp:184-199);
+//   * lane streams are sorted by length and packed 32 at a time into SLICES; a slice is padded
+//     to its longest stream (rounded up to 4), which after sorting costs a few percent, and is
+//     stored so that each warp-wide 128-bit value load / 64-bit column load is one contiguous
+//     512 B / 256 B run: vals[len/4][32 lanes][4], cols[len/4][32 lanes][4];
+//   * slice_rows[s][lane] is the matrix row a lane's partial sum is added to (the row the
+//     reference recovers by counting end-of-row markers, spmv/libfpga/spmv_cluster.h:78-83);
+//     no in-band markers are needed.
 //
-// 6 bytes per non-zero + 4 bytes per non-empty (row, tile) segment + 8 bytes per 256 non-zeros.
+// 6 bytes per stored non-zero slot + 4 bytes per lane stream + 8 bytes per slice.
 #ifndef HISPARSE_B200_TILE_FORMAT_H_
 #define HISPARSE_B200_TILE_FORMAT_H_
 
@@ -29,45 +33,55 @@
 namespace hsb {
 
 constexpr int kLanes = 32;
-constexpr int kNnzPerLane = 8;
-constexpr int kChunkNnz = kLanes * kNnzPerLane;          // 256
-constexpr uint32_t kMaxTileCols = 32768;                 // 15-bit local column id, 128 KB of x
-constexpr uint16_t kSegEndFlag = 0x8000;
-constexpr uint32_t kChunkContinues = 0x80000000u;        // ChunkDesc.tile bit: real non-zeros follow the last flag
+constexpr int kSlotBlock = 4;                            // non-zeros per lane per load step
+constexpr int kStepElems = kLanes * kSlotBlock;          // 128 elements per slice step
+constexpr uint32_t kMaxStreamLen = 128;                  // non-zeros per lane stream (keeps 32-bit partial sums exact)
+constexpr uint32_t kMaxTileCols = 32768;                 // 128 KB of x in shared memory
+constexpr uint16_t kPadCol = 0x8000;                     // column id of padding slots: xs[32768] is a constant 0 word
 
-struct ChunkDesc {
-    uint32_t seg_base;      // global index (into seg_row) of the segment open at the start of the chunk
-    uint32_t tile;          // tile index | kChunkContinues
+struct SliceDesc {
+    uint32_t off;           // element offset of the slice / kStepElems
+    uint32_t tile_steps;    // (tile index << 8) | steps, steps = padded stream length / 4  (1..32)
 };
 
 struct TileDesc {
     uint32_t col_base;      // first column of the tile (multiple of 8)
     uint32_t col_count;     // columns in the tile, rounded up to a multiple of 8
-    uint32_t chunk_begin;   // [chunk_begin, chunk_end) in the global chunk stream
-    uint32_t chunk_end;
+    uint32_t slice_begin;   // [slice_begin, slice_end) in the global slice list
+    uint32_t slice_end;
     uint32_t row_part;      // row partition the tile belongs to
-    uint32_t pad_[3];
+    uint32_t step_begin;    // element offset of the tile's first slice / kStepElems
+    uint32_t pad_[2];
+    // Slices of a tile are sorted by length, so the whole per-slice geometry is 32 numbers:
+    // cnt_ge[c] = slices of this tile with more than c steps. Slice i (tile-relative) has
+    // steps(i) = #{c : cnt_ge[c] > i} and starts at step S(i) = sum_c min(i, cnt_ge[c]).
+    uint32_t cnt_ge[32];
 };
+constexpr int kMaxSteps = 32;
 
 struct TiledMatrix {
     uint32_t rows = 0, cols = 0;            // as given (rows may include padding rows)
     uint64_t nnz = 0;
     uint32_t rows_per_part = 0, n_row_parts = 0, n_col_tiles = 0, tile_cols = 0;
-    std::vector<uint32_t> vals;             // n_chunks * 256 words, warp-transposed inside a chunk
-    std::vector<uint16_t> cidx;             // n_chunks * 256 : local column | end-of-segment flag
-    std::vector<ChunkDesc> chunks;          // n_chunks
-    std::vector<uint32_t> seg_row;          // n_segments
+    uint64_t n_streams = 0;                 // lane streams (row segments after splitting)
+    std::vector<uint32_t> vals;             // n_elems words
+    std::vector<uint16_t> cols16;           // n_elems local column ids
+    std::vector<SliceDesc> slices;          // n_slices (host side only: planning and inspection)
+    std::vector<uint32_t> slice_rows;       // n_slices * 32 ; `rows` (one past the end) marks an unused lane
     std::vector<TileDesc> tiles;            // n_row_parts * n_col_tiles, row-partition major
-    std::vector<uint32_t> part_chunk_begin; // n_row_parts + 1
-    size_t n_chunks() const { return chunks.size(); }
+    std::vector<uint32_t> part_slice_begin; // n_row_parts + 1
+    size_t n_slices() const { return slices.size(); }
+    size_t n_elems() const { return vals.size(); }
     size_t format_bytes() const {
-        return vals.size() * 4 + cidx.size() * 2 + chunks.size() * sizeof(ChunkDesc) + seg_row.size() * 4 +
-               tiles.size() * sizeof(TileDesc);
+        // what the kernel reads from HBM (the SliceDesc list stays on the host)
+        return vals.size() * 4 + cols16.size() * 2 + slice_rows.size() * 4 + tiles.size() * sizeof(TileDesc);
     }
 };
 
-// position of the k-th (0..7) non-zero of lane l inside a chunk's value block
-inline size_t val_slot(int lane, int k) { return (size_t)((k >> 2) * kLanes + lane) * 4 + (k & 3); }
+// element index of slot k (0..len-1) of lane l inside a slice that starts at element `base`
+inline size_t slice_elem(size_t base, int lane, uint32_t k) {
+    return base + (size_t)(k / kSlotBlock) * kStepElems + (size_t)lane * kSlotBlock + (k % kSlotBlock);
+}
 
 // Choose a tile width: the fewest tiles of <= kMaxTileCols columns, widths equalised, multiple of 8.
 uint32_t choose_tile_cols(uint32_t cols);
@@ -77,6 +91,18 @@ uint32_t choose_tile_cols(uint32_t cols);
 bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uint32_t *indices,
                  const uint32_t *vals, uint32_t rows_per_part, uint32_t tile_cols, int n_threads,
                  TiledMatrix *out, std::string *err);
+
+// A unit of CTA work: steps [t_lo, t_hi) (tile-relative) of one tile. A CTA stages the tile's x
+// once per segment.
+struct Segment {
+    uint32_t tile, t_lo, t_hi, pad_;
+};
+// Work plan for one launch over tiles [tile_begin, tile_end) on `ctas` CTAs: CTA b runs
+// segs[cta_seg[b] .. cta_seg[b+1]). Cuts are placed at equal cost (steps + one unit per slice,
+// the latter paying for the slice's 32 row updates) and may fall inside a slice; when there are
+// no more tiles than CTAs no CTA works on two tiles (a second x staging would double its time).
+void plan_launch(const TiledMatrix &m, uint32_t tile_begin, uint32_t tile_end, uint32_t ctas,
+                 std::vector<uint32_t> *cta_seg, std::vector<Segment> *segs);
 
 }  // namespace hsb
 #endif

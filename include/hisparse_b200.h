@@ -57,7 +57,9 @@ typedef struct hsb_stats {
     uint64_t nnz;                  /* non-zeros of the resident matrix */
     uint32_t rows, cols;           /* padded dimensions */
     uint32_t n_row_parts, n_col_tiles, tile_cols;
-    uint64_t n_chunks, n_segments;
+    uint64_t n_slices;             /* warp work units: 32 lane streams each */
+    uint64_t n_streams;            /* lane streams = row segments after splitting long rows */
+    uint64_t n_elems;              /* stored non-zero slots including padding */
     uint64_t format_bytes;         /* bytes of the tile-stream format in HBM */
     uint64_t algorithmic_bytes;    /* 8*nnz + 4*(rows+1) + 4*rows + 4*cols   */
     uint64_t kernel_launches;      /* kernels of this library launched so far on this context */
@@ -104,7 +106,9 @@ int hsb_upload_vector(hsb_ctx *ctx, const void *x_packed, unsigned num_cols);
 int hsb_spmv_row_partition(hsb_ctx *ctx, unsigned row_part_id, unsigned part_len,
                            unsigned num_col_partitions, unsigned num_partitions, unsigned num_cols);
 
-/* all row partitions back to back (the loop at sw/benchmark.cpp:317-340), asynchronous */
+/* all row partitions back to back (the loop at sw/benchmark.cpp:317-340), asynchronous.
+ * The packed result becomes final on the device at the next hsb_sync() / hsb_download_result()
+ * (or inside the next hsb_spmv*, which drains its predecessor's row accumulators first). */
 int hsb_spmv(hsb_ctx *ctx);
 int hsb_sync(hsb_ctx *ctx);
 
@@ -128,7 +132,12 @@ int hsb_set_replicas(hsb_ctx *ctx, int n);
  * step_ms = (stop - start) / steps over the whole loop; kernel_ms = mean duration of the main
  * tile kernel alone, from per-launch event pairs in a second loop of the same length. */
 int hsb_time_spmv(hsb_ctx *ctx, int warmup, int steps, float *step_ms, float *kernel_ms);
-/* raw device pointers / stream for callers that move x or y with NCCL (torch.distributed) */
+/* Profiling aid: SM-clock stamps of the last launch, [sm_count][34] = per warp "my slices are done",
+ * then CTA "arrived at the grid barrier", then "drain done". out == NULL arms (capacity != 0) or
+ * disarms (capacity == 0) the trace and returns the number of words. */
+int hsb_debug_trace(hsb_ctx *ctx, unsigned long long *out, size_t capacity);
+/* raw device pointers / stream for callers that move x or y with NCCL (torch.distributed);
+ * call hsb_sync() before reading device y */
 void *hsb_device_x(hsb_ctx *ctx);
 void *hsb_device_y(hsb_ctx *ctx);
 void *hsb_stream(hsb_ctx *ctx);

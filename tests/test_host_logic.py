@@ -66,9 +66,9 @@ def test_tile_format_round_trip(name, mat, rpp, tile):
     a = _canon(rows, indptr, indices, np.ascontiguousarray(data).view(np.uint32))
     b = _canon(rows, ip, ix, vv)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
-    # bytes: 6 per non-zero slot + 4 per segment + 8 per chunk (+ tile table)
-    assert st["format_bytes"] >= 6 * st["nnz"]
-    assert st["n_segments"] <= max(1, rows * st["n_col_tiles"])
+    # bytes: 6 per stored slot + 4 per lane stream slot + 8 per slice (+ tile table)
+    assert st["format_bytes"] >= 6 * st["nnz"] and st["n_elems"] >= st["nnz"]
+    assert st["n_streams"] <= max(1, rows * st["n_col_tiles"]) + st["nnz"] // 64 + 1
 
 
 def test_format_rejects_malformed():
