@@ -158,7 +158,7 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
     const uint32_t G = (uint32_t)c->sm_count;
     const int grid = (int)c->plan_grid[slot];
     hsb::SpmvParams p;
-    p.vals = m.vals; p.cols = m.cols; p.slice_rows = m.slice_rows; p.tiles = m.tiles;
+    p.vals = m.vals; p.cols = m.cols; p.slice_rows = m.slice_rows;
     p.cta_seg = c->d_cta_seg + slot * (size_t)(G + 1);
     p.segs = c->d_segs;
     p.x = c->d_x; p.y = c->d_y;

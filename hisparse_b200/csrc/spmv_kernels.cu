@@ -133,10 +133,11 @@ __device__ __forceinline__ uint32_t slice_of_step(uint32_t cnt, uint32_t n_slice
 // One warp streams tile-relative steps [ta, tb): a flat, contiguous run of (512 B values + 256 B
 // columns) steps that may start and end inside a slice. Lanes own lane streams; whenever a slice
 // (or the run) ends, the lane's partial sum is added to its row and the accumulator restarts.
-template <class A>
+template <class A, class F>
 __device__ __forceinline__ void stream_steps(const SpmvParams &p, const uint32_t *xs, uint64_t *bar, uint32_t parity,
                                              uint32_t cnt, uint32_t slice_begin, uint32_t n_slices,
-                                             uint32_t step_begin, uint32_t ta, uint32_t tb, uint32_t lane) {
+                                             uint32_t step_begin, uint32_t ta, uint32_t tb, uint32_t lane,
+                                             bool first_segment, F &before_x_wait) {
     uint32_t remaining = tb - ta;
     const size_t base = (size_t)(step_begin + ta) * kStepElems;
     const uint4 *vp = reinterpret_cast<const uint4 *>(p.vals + base) + lane;
@@ -164,6 +165,7 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, const uint32_t
         if (sl + 1 < n_slices) row_next = __ldg(rp + kLanes);
     }
 
+    if (first_segment) before_x_wait();                      // previous launch complete; drain its sums
     mbar_wait(bar, parity);
     if (!remaining) return;
 
@@ -229,14 +231,22 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_tiles_kernel(const SpmvParam
 
     // Drain the previous launch's accumulators (clamp / copy into y, re-zero): the pe dump + result
     // drain of the reference (pe.h:95-116, spmv_result_drain.cpp) and the PE's reset loop
-    // (pe.h:131-135). The kernel boundary is the barrier that makes those sums final, and this
-    // launch accumulates into the other buffer, so the drain overlaps the x staging below.
+    // (pe.h:131-135). The previous launch is complete once griddepcontrol.wait returns, and this
+    // launch accumulates into the other buffer, so the drain overlaps the x staging.
     auto drain = [&]() {
         if (p.drain_acc) {
             for (uint32_t r = p.drain_begin + blockIdx.x * kThreads + tid; r < p.drain_end; r += gridDim.x * kThreads)
                 p.y[r] = A::drain(p.drain_acc, r);
             if (blockIdx.x == 0 && tid == 0) (void)A::drain(p.drain_acc, p.trash_row);
         }
+    };
+    // Programmatic dependent launch: everything above the wait (work-plan loads, x staging, the
+    // first matrix loads) only reads data no kernel writes, so it runs while the previous launch's
+    // slower CTAs are still finishing on other SMs.
+    auto wait_for_previous_launch = [&]() {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        drain();
     };
 
     if (g0 < g1) {
@@ -247,32 +257,30 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_tiles_kernel(const SpmvParam
         __syncthreads();
         uint32_t parity = 0;
         for (uint32_t g = g0; g < g1; g++) {
-            const uint4 sg = __ldg(reinterpret_cast<const uint4 *>(p.segs + g));   // tile, t_lo, t_hi
-            const TileDesc *td = p.tiles + sg.x;
-            const uint32_t cnt = __ldg(&td->cnt_ge[lane]);
-            const uint32_t slice_begin = __ldg(&td->slice_begin);
-            const uint32_t n_slices = __ldg(&td->slice_end) - slice_begin;
+            const Segment *sg = p.segs + g;
+            const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(sg));        // tile, t_lo, t_hi, col_base
+            const uint4 h1 = __ldg(reinterpret_cast<const uint4 *>(sg) + 1);    // col_count, slice_begin, n_slices, step_begin
+            const uint32_t cnt = __ldg(&sg->cnt_ge[lane]);
             // stage the x tile: the vector loader + vecbuf writer of the reference
             if (tid == 0) {
                 fence_proxy_async();
-                const uint32_t bytes = __ldg(&td->col_count) * 4u;
+                const uint32_t bytes = h1.x * 4u;
                 mbar_arrive_expect_tx(&bar, bytes);
-                const unsigned char *src = reinterpret_cast<const unsigned char *>(p.x + __ldg(&td->col_base));
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(p.x + h0.w);
                 for (uint32_t off = 0; off < bytes; off += kBulkPiece)
                     bulk_g2s(smem_raw + off, src + off, min(kBulkPiece, bytes - off), &bar);
             }
-            if (g == g0) drain();
             // equal shares of the segment's steps for the warps
-            const uint32_t n = sg.z - sg.y;
-            const uint32_t ta = sg.y + (uint32_t)(((unsigned long long)n * warp) / kWarps);
-            const uint32_t tb = sg.y + (uint32_t)(((unsigned long long)n * (warp + 1)) / kWarps);
-            stream_steps<A>(p, xs, &bar, parity, cnt, slice_begin, n_slices, __ldg(&td->step_begin), ta, tb, lane);
+            const uint32_t n = h0.z - h0.y;
+            const uint32_t ta = h0.y + (uint32_t)(((unsigned long long)n * warp) / kWarps);
+            const uint32_t tb = h0.y + (uint32_t)(((unsigned long long)n * (warp + 1)) / kWarps);
+            stream_steps<A>(p, xs, &bar, parity, cnt, h1.y, h1.z, h1.w, ta, tb, lane, g == g0, wait_for_previous_launch);
             parity ^= 1u;
             if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * (kWarps + 2) + warp] = clock64() - t_start;
             __syncthreads();                                       // everyone is done with this x tile
         }
     } else {
-        drain();
+        wait_for_previous_launch();
     }
     if (p.trace && tid == 0) p.trace[(size_t)blockIdx.x * (kWarps + 2) + kWarps] = clock64() - t_start;
 }
@@ -295,11 +303,18 @@ cudaError_t configure_kernels() {
 }
 
 cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, cudaStream_t stream) {
-    if (arith == kArithFixed)
-        spmv_tiles_kernel<FixedArith><<<grid, kThreads, kSmemBytes, stream>>>(p);
-    else
-        spmv_tiles_kernel<FloatArith><<<grid, kThreads, kSmemBytes, stream>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see griddepcontrol.wait in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (arith == kArithFixed) return cudaLaunchKernelEx(&cfg, spmv_tiles_kernel<FixedArith>, p);
+    return cudaLaunchKernelEx(&cfg, spmv_tiles_kernel<FloatArith>, p);
 }
 
 cudaError_t launch_drain(int arith, void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end,

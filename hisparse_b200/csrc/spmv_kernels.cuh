@@ -50,9 +50,8 @@ struct SpmvParams {
     const uint32_t *vals;
     const uint16_t *cols;
     const uint32_t *slice_rows;
-    const TileDesc *tiles;
     const uint32_t *cta_seg;      // gridDim.x + 1 : CTA b runs segs[cta_seg[b] .. cta_seg[b+1])
-    const Segment *segs;          // (tile, [t_lo, t_hi) tile-relative steps): one x staging each
+    const Segment *segs;          // (tile, [t_lo, t_hi) tile-relative steps, tile geometry): one x staging each
     const uint32_t *x;            // packed dense vector, raw 32-bit words
     void *acc;                    // row accumulators of THIS launch (uint64 fixed / fp32 float), rows + 1 entries,
                                   // all zero on entry

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -244,21 +245,53 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
     for (uint32_t j = 0; j <= M.n_row_parts; j++) M.part_slice_begin[j] = (uint32_t)t_slices[(size_t)j * T];
 
     // ---- stage C -------------------------------------------------------------------------
+    // The order of the non-zeros inside a lane stream is free (fixed point: the sum is order
+    // independent; float: within tolerance), so it is chosen here such that the 32 lanes of a slice
+    // gather from 32 different shared-memory banks (bank = column % 32) at every slot whenever
+    // possible. This is the reference's shuffle unit #1 (spmv/libfpga/shuffle.h:24-99: an arbiter
+    // that grants one request per vector-buffer bank per cycle and re-sends the losers) done once,
+    // offline, instead of dynamically in hardware.
     const size_t kBlock = 256;                               // slices per task
     parallel_for((NSL + kBlock - 1) / kBlock, n_threads, [&](size_t blk) {
+        std::vector<uint32_t> v((size_t)kLanes * kMaxStreamLen);
+        std::vector<uint16_t> cidx((size_t)kLanes * kMaxStreamLen);
         for (size_t s = blk * kBlock; s < std::min(NSL, (blk + 1) * kBlock); s++) {
             const size_t ti = M.slices[s].tile_steps >> 8;
             const uint64_t i0 = t_streams[ti] + (s - t_slices[ti]) * kLanes;
             const size_t base = (size_t)M.slices[s].off * kStepElems;
+            uint32_t rem[kLanes], maxlen = 0;
             for (int lane = 0; lane < kLanes; lane++) {
+                rem[lane] = 0;
                 uint64_t i = i0 + lane;
-                if (i >= t_streams[ti + 1]) break;
+                if (i >= t_streams[ti + 1]) continue;
                 const Stream &st = streams[i];
                 M.slice_rows[s * kLanes + lane] = st.row;
+                rem[lane] = st.len;
+                maxlen = std::max(maxlen, st.len);
                 for (uint32_t k = 0; k < st.len; k++) {
-                    size_t e = slice_elem(base, lane, k);
-                    M.vals[e] = a_vals[st.src + k];
-                    M.cols16[e] = a_cols[st.src + k];
+                    v[(size_t)lane * kMaxStreamLen + k] = a_vals[st.src + k];
+                    cidx[(size_t)lane * kMaxStreamLen + k] = a_cols[st.src + k];
+                }
+            }
+            for (uint32_t k = 0; k < maxlen; k++) {
+                uint32_t busy = 0;                              // banks granted at this slot
+                for (int q = 0; q < kLanes; q++) {
+                    const int lane = (q + (int)k) & (kLanes - 1);    // rotating priority, like the arbiter
+                    uint32_t n = rem[lane];
+                    if (!n) continue;
+                    uint32_t *lv = &v[(size_t)lane * kMaxStreamLen];
+                    uint16_t *lc = &cidx[(size_t)lane * kMaxStreamLen];
+                    uint32_t pick = 0;
+                    const uint32_t window = std::min(n, 16u);
+                    for (uint32_t c = 0; c < window; c++)
+                        if (!((busy >> (lc[c] & 31u)) & 1u)) { pick = c; break; }
+                    busy |= 1u << (lc[pick] & 31u);
+                    const size_t e = slice_elem(base, lane, k);
+                    M.vals[e] = lv[pick];
+                    M.cols16[e] = lc[pick];
+                    lv[pick] = lv[n - 1];                       // order inside a stream is free
+                    lc[pick] = lc[n - 1];
+                    rem[lane] = n - 1;
                 }
             }
         }
@@ -267,12 +300,23 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
 }
 
 namespace {
-// tile-relative step position at which the cost prefix (steps + slices started) of tile `td` reaches w
+// cost of finishing a slice (row-id load, warp vote, up to 32 row updates) in units of one step
+// (768 B of matrix stream); fitted to per-CTA traces on B200. HSB_SLICE_COST overrides for tuning.
+double slice_cost() {
+    static const double v = [] {
+        const char *e = std::getenv("HSB_SLICE_COST");
+        return e ? std::atof(e) : 1.5;
+    }();
+    return v;
+}
+// tile-relative step position at which the cost prefix (steps + kSliceCost * slices started) of
+// tile `td` reaches w
 uint32_t step_at_cost(const TiledMatrix &m, const TileDesc &td, double w) {
-    // cost prefix before slice i: S(i) + i ; inside slice i after k steps: S(i) + i + 1 + k
+    const double B = slice_cost();
+    // cost prefix before slice i: S(i) + B*i ; inside slice i after k steps: S(i) + B*i + B + k
     uint32_t lo = 0, hi = td.slice_end - td.slice_begin;       // find last slice whose start cost <= w
     auto start_cost = [&](uint32_t i) {
-        return (double)(m.slices[td.slice_begin + i].off - td.step_begin) + i;
+        return (double)(m.slices[td.slice_begin + i].off - td.step_begin) + B * i;
     };
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) / 2;
@@ -280,7 +324,7 @@ uint32_t step_at_cost(const TiledMatrix &m, const TileDesc &td, double w) {
     }
     const SliceDesc &sd = m.slices[td.slice_begin + lo];
     uint32_t steps = sd.tile_steps & 0xFFu, s_before = sd.off - td.step_begin;
-    double inside = w - start_cost(lo) - 1.0;
+    double inside = w - start_cost(lo) - B;
     uint32_t k = inside <= 0 ? 0u : (uint32_t)std::min<double>(steps, inside + 0.5);
     return s_before + k;
 }
@@ -288,6 +332,18 @@ uint32_t tile_steps_total(const TiledMatrix &m, const TileDesc &td) {
     if (td.slice_end == td.slice_begin) return 0;
     const SliceDesc &last = m.slices[td.slice_end - 1];
     return last.off + (last.tile_steps & 0xFFu) - td.step_begin;
+}
+}  // namespace
+
+namespace {
+Segment make_segment(const TiledMatrix &m, uint32_t tile, uint32_t t_lo, uint32_t t_hi) {
+    const TileDesc &td = m.tiles[tile];
+    Segment g;
+    g.tile = tile; g.t_lo = t_lo; g.t_hi = t_hi;
+    g.col_base = td.col_base; g.col_count = td.col_count; g.slice_begin = td.slice_begin;
+    g.n_slices = td.slice_end - td.slice_begin; g.step_begin = td.step_begin;
+    std::memcpy(g.cnt_ge, td.cnt_ge, sizeof g.cnt_ge);
+    return g;
 }
 }  // namespace
 
@@ -301,7 +357,7 @@ void plan_launch(const TiledMatrix &m, uint32_t tile_begin, uint32_t tile_end, u
         const TileDesc &td = m.tiles[t];
         if (td.slice_end == td.slice_begin) continue;
         live.push_back(t);
-        cost.push_back((double)tile_steps_total(m, td) + (td.slice_end - td.slice_begin));
+        cost.push_back((double)tile_steps_total(m, td) + slice_cost() * (td.slice_end - td.slice_begin));
         total += cost.back();
     }
     if (live.empty() || ctas == 0) return;
@@ -327,7 +383,7 @@ void plan_launch(const TiledMatrix &m, uint32_t tile_begin, uint32_t tile_end, u
             for (uint32_t k = 1; k <= n[i]; k++) {
                 uint32_t cut = k == n[i] ? steps : std::max(prev, std::min(steps, step_at_cost(m, td, cost[i] * k / n[i])));
                 (*cta_seg)[b] = (uint32_t)segs->size();
-                if (cut > prev) segs->push_back(Segment{live[i], prev, cut, 0});
+                if (cut > prev) segs->push_back(make_segment(m, live[i], prev, cut));
                 b++;
                 prev = cut;
             }
@@ -347,14 +403,14 @@ void plan_launch(const TiledMatrix &m, uint32_t tile_begin, uint32_t tile_end, u
             const TileDesc &td = m.tiles[live[i]];
             const uint32_t steps = tile_steps_total(m, td);
             if (b + 1 == ctas || done + cost[i] <= target) {            // the rest of this tile
-                if (steps > prev) segs->push_back(Segment{live[i], prev, steps, 0});
+                if (steps > prev) segs->push_back(make_segment(m, live[i], prev, steps));
                 done += cost[i];
                 i++;
                 prev = 0;
                 continue;
             }
             uint32_t cut = std::max(prev, std::min(steps, step_at_cost(m, td, target - done)));
-            if (cut > prev) segs->push_back(Segment{live[i], prev, cut, 0});
+            if (cut > prev) segs->push_back(make_segment(m, live[i], prev, cut));
             prev = cut;
             break;
         }

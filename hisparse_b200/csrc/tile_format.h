@@ -95,7 +95,11 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
 // A unit of CTA work: steps [t_lo, t_hi) (tile-relative) of one tile. A CTA stages the tile's x
 // once per segment.
 struct Segment {
-    uint32_t tile, t_lo, t_hi, pad_;
+    uint32_t tile, t_lo, t_hi;
+    // copy of the tile's geometry, so that a CTA needs ONE dependent load before it can start
+    // streaming: column range of the x tile, slice list, first step, and the slice-length table
+    uint32_t col_base, col_count, slice_begin, n_slices, step_begin;
+    uint32_t cnt_ge[32];
 };
 // Work plan for one launch over tiles [tile_begin, tile_end) on `ctas` CTAs: CTA b runs
 // segs[cta_seg[b] .. cta_seg[b+1]). Cuts are placed at equal cost (steps + one unit per slice,
