@@ -244,3 +244,16 @@ def test_fixed_googleplus_size(gpu, port):
     assert np.all(y2 >= y1)
     assert np.array_equal(y2, port.spmv_q824(ip2, indices, words, xw2))
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------
+# the C++ host drivers (hisparse_b200/host/host.cpp == the reference's sw/host.cpp flow)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", hsoracle.IMPLS)
+def test_cpp_host_driver(gpu, impl):
+    import subprocess
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hisparse_b200", "host")
+    subprocess.run(["make", "-s", "-C", host], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(host, "bin", "host_" + impl)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "===== All Test Passed! =====" in r.stdout
