@@ -120,24 +120,14 @@ __device__ __forceinline__ uint32_t steps_before(uint32_t cnt, uint32_t i) {
 __device__ __forceinline__ uint32_t steps_of(uint32_t cnt, uint32_t i) {
     return __popc(__ballot_sync(0xFFFFFFFFu, cnt > i));
 }
-// tile-relative slice that contains step t: the largest i with S(i) <= t  (0 <= i < n_slices)
-__device__ __forceinline__ uint32_t slice_of_step(uint32_t cnt, uint32_t n_slices, uint32_t t) {
-    uint32_t lo = 0, hi = n_slices;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (steps_before(cnt, mid) <= t) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
 // One warp streams tile-relative steps [ta, tb): a flat, contiguous run of (512 B values + 256 B
 // columns) steps that may start and end inside a slice. Lanes own lane streams; whenever a slice
 // (or the run) ends, the lane's partial sum is added to its row and the accumulator restarts.
 template <class A, class F>
 __device__ __forceinline__ void stream_steps(const SpmvParams &p, const uint32_t *xs, uint64_t *bar, uint32_t parity,
                                              uint32_t cnt, uint32_t slice_begin, uint32_t n_slices,
-                                             uint32_t step_begin, uint32_t ta, uint32_t tb, uint32_t lane,
-                                             bool first_segment, F &before_x_wait) {
+                                             uint32_t step_begin, uint32_t ta, uint32_t tb, uint32_t first_slice,
+                                             uint32_t lane, bool first_segment, F &before_x_wait) {
     uint32_t remaining = tb - ta;
     const size_t base = (size_t)(step_begin + ta) * kStepElems;
     const uint4 *vp = reinterpret_cast<const uint4 *>(p.vals + base) + lane;
@@ -158,7 +148,7 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, const uint32_t
     uint32_t sl = 0, left = 0, row = 0, row_next = 0;
     const uint32_t *rp = p.slice_rows;
     if (remaining) {
-        sl = slice_of_step(cnt, n_slices, ta);
+        sl = first_slice;                                     // the slice that contains step ta (host plan)
         left = steps_before(cnt, sl + 1) - ta;                // steps of slice sl still ahead of us
         rp = p.slice_rows + (size_t)(slice_begin + sl) * kLanes + lane;
         row = __ldg(rp);
@@ -270,11 +260,11 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_tiles_kernel(const SpmvParam
                 for (uint32_t off = 0; off < bytes; off += kBulkPiece)
                     bulk_g2s(smem_raw + off, src + off, min(kBulkPiece, bytes - off), &bar);
             }
-            // equal shares of the segment's steps for the warps
-            const uint32_t n = h0.z - h0.y;
-            const uint32_t ta = h0.y + (uint32_t)(((unsigned long long)n * warp) / kWarps);
-            const uint32_t tb = h0.y + (uint32_t)(((unsigned long long)n * (warp + 1)) / kWarps);
-            stream_steps<A>(p, xs, &bar, parity, cnt, h1.y, h1.z, h1.w, ta, tb, lane, g == g0, wait_for_previous_launch);
+            // this warp's equal-cost share of the segment (host plan)
+            const uint32_t ta = __ldg(&sg->warp_t[warp]), tb = __ldg(&sg->warp_t[warp + 1]);
+            const uint32_t first_slice = __ldg(&sg->warp_slice[warp]);
+            stream_steps<A>(p, xs, &bar, parity, cnt, h1.y, h1.z, h1.w, ta, tb, first_slice, lane, g == g0,
+                            wait_for_previous_launch);
             parity ^= 1u;
             if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * (kWarps + 2) + warp] = clock64() - t_start;
             __syncthreads();                                       // everyone is done with this x tile

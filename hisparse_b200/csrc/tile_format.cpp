@@ -299,7 +299,6 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
     return true;
 }
 
-namespace {
 // cost of finishing a slice (row-id load, warp vote, up to 32 row updates) in units of one step
 // (768 B of matrix stream); fitted to per-CTA traces on B200. HSB_SLICE_COST overrides for tuning.
 double slice_cost() {
@@ -309,6 +308,7 @@ double slice_cost() {
     }();
     return v;
 }
+namespace {
 // tile-relative step position at which the cost prefix (steps + kSliceCost * slices started) of
 // tile `td` reaches w
 uint32_t step_at_cost(const TiledMatrix &m, const TileDesc &td, double w) {
@@ -336,13 +336,39 @@ uint32_t tile_steps_total(const TiledMatrix &m, const TileDesc &td) {
 }  // namespace
 
 namespace {
+// tile-relative slice containing step t (t < total steps of the tile)
+uint32_t slice_of_step_host(const TiledMatrix &m, const TileDesc &td, uint32_t t) {
+    uint32_t lo = 0, hi = td.slice_end - td.slice_begin;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) / 2;
+        if (m.slices[td.slice_begin + mid].off - td.step_begin <= t) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+// cost of everything before tile-relative step t
+double cost_at_step(const TiledMatrix &m, const TileDesc &td, uint32_t t) {
+    if (td.slice_end == td.slice_begin) return 0;
+    if (t >= tile_steps_total(m, td)) return tile_steps_total(m, td) + slice_cost() * (td.slice_end - td.slice_begin);
+    uint32_t i = slice_of_step_host(m, td, t);
+    uint32_t s0 = m.slices[td.slice_begin + i].off - td.step_begin;
+    return t + slice_cost() * (i + (t > s0 ? 1 : 0));
+}
 Segment make_segment(const TiledMatrix &m, uint32_t tile, uint32_t t_lo, uint32_t t_hi) {
     const TileDesc &td = m.tiles[tile];
     Segment g;
+    std::memset(&g, 0, sizeof g);
     g.tile = tile; g.t_lo = t_lo; g.t_hi = t_hi;
     g.col_base = td.col_base; g.col_count = td.col_count; g.slice_begin = td.slice_begin;
     g.n_slices = td.slice_end - td.slice_begin; g.step_begin = td.step_begin;
     std::memcpy(g.cnt_ge, td.cnt_ge, sizeof g.cnt_ge);
+    const double c0 = cost_at_step(m, td, t_lo), c1 = cost_at_step(m, td, t_hi);
+    const uint32_t total = tile_steps_total(m, td);
+    for (int w = 0; w <= 32; w++) {
+        uint32_t t = w == 0 ? t_lo : (w == 32 ? t_hi : step_at_cost(m, td, c0 + (c1 - c0) * w / 32.0));
+        t = std::min(std::max(t, w ? g.warp_t[w - 1] : t_lo), t_hi);
+        g.warp_t[w] = t;
+        if (w < 32) g.warp_slice[w] = t < total ? slice_of_step_host(m, td, t) : g.n_slices;
+    }
     return g;
 }
 }  // namespace

@@ -100,11 +100,19 @@ struct Segment {
     // streaming: column range of the x tile, slice list, first step, and the slice-length table
     uint32_t col_base, col_count, slice_begin, n_slices, step_begin;
     uint32_t cnt_ge[32];
+    // equal-cost shares of [t_lo, t_hi) for the CTA's 32 warps: warp w streams steps
+    // [warp_t[w], warp_t[w+1]) and starts inside tile-relative slice warp_slice[w]
+    uint32_t warp_t[33];
+    uint32_t warp_slice[32];
+    uint32_t pad_[3];
 };
+static_assert(sizeof(Segment) % 16 == 0, "Segment is loaded with 128-bit loads");
 // Work plan for one launch over tiles [tile_begin, tile_end) on `ctas` CTAs: CTA b runs
 // segs[cta_seg[b] .. cta_seg[b+1]). Cuts are placed at equal cost (steps + one unit per slice,
 // the latter paying for the slice's 32 row updates) and may fall inside a slice; when there are
 // no more tiles than CTAs no CTA works on two tiles (a second x staging would double its time).
+// cost of finishing a slice in units of one step (HSB_SLICE_COST overrides the fitted default)
+double slice_cost();
 void plan_launch(const TiledMatrix &m, uint32_t tile_begin, uint32_t tile_end, uint32_t ctas,
                  std::vector<uint32_t> *cta_seg, std::vector<Segment> *segs);
 
