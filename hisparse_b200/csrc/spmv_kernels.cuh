@@ -7,7 +7,7 @@
 //   ------------------------------------------------    --------------------------------------------
 //   spmv_vector_loader + axis_duplicate + vecbuf_writer x tile -> shared memory with cp.async.bulk
 //     (spmv_vector_loader.cpp:7-79, stream_utils.h:8,     (TMA bulk copy, mbarrier complete_tx);
-//      vecbuf_access_unit.h:92-136)                       one <=128 KB tile = LOGICAL_VB_SIZE words
+//      vecbuf_access_unit.h:92-136)                       one <= 224 KB tile (the reference: 128 KB = LOGICAL_VB_SIZE words)
 //   CPSR_matrix_loader (spmv_cluster.h:34-107)          every warp streams ONE contiguous run of slice steps
 //                                                         with 128-bit / 64-bit ld.global.nc loads (each
 //                                                         warp-wide load a contiguous 512 / 256 B), a
@@ -41,7 +41,7 @@ namespace hsb {
 
 constexpr int kThreads = 1024;                       // 32 warps: one CTA per SM
 constexpr int kWarps = kThreads / 32;
-constexpr uint32_t kXTileBytes = kMaxTileCols * 4;   // 128 KB
+constexpr uint32_t kXTileBytes = kMaxTileCols * 4;   // 224 KB
 constexpr uint32_t kSmemBytes = kXTileBytes + 16;    // + the constant-zero word padding slots gather
 constexpr uint32_t kBulkPiece = 16384;               // bytes per cp.async.bulk
 constexpr int kPrefetch = 4;                         // slice steps in flight per warp

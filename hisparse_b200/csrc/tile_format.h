@@ -6,9 +6,10 @@
 // 32-wide warps, 128-byte coalescing and a load-balanced persistent grid:
 //
 //   * rows are cut into row partitions (the reference's LOGICAL_OB_SIZE cut,
-//     sw/data_formatter.h:494), columns into tiles of <= 32768 columns (the reference's
-//     LOGICAL_VB_SIZE = 32768-word vector buffer, spmv/libfpga/common.h:165,179) so that the
-//     x tile of a work unit fits in one CTA's shared memory and a local column id fits 16 bits;
+//     sw/data_formatter.h:494), columns into tiles of <= 57344 columns (the role of the
+//     reference's LOGICAL_VB_SIZE = 32768-word vector buffer, spmv/libfpga/common.h:165,179, sized
+//     for B200's 227 KB of shared memory per CTA) so that the x tile of a work unit fits in one
+//     CTA's shared memory and a local column id fits 16 bits;
 //   * inside a (row partition, column tile) every non-empty row segment becomes one or more
 //     LANE STREAMS of at most kMaxStreamLen non-zeros (long rows are split so that no lane
 //     serialises a hub row -- the reference instead pads every lane to the longest,
@@ -36,8 +37,8 @@ constexpr int kLanes = 32;
 constexpr int kSlotBlock = 4;                            // non-zeros per lane per load step
 constexpr int kStepElems = kLanes * kSlotBlock;          // 128 elements per slice step
 constexpr uint32_t kMaxStreamLen = 128;                  // non-zeros per lane stream (keeps 32-bit partial sums exact)
-constexpr uint32_t kMaxTileCols = 32768;                 // 128 KB of x in shared memory
-constexpr uint16_t kPadCol = 0x8000;                     // column id of padding slots: xs[32768] is a constant 0 word
+constexpr uint32_t kMaxTileCols = 57344;                 // 224 KB of x in shared memory (of 227 KB per CTA), 16-bit ids
+constexpr uint16_t kPadCol = 57344;                      // column id of padding slots: xs[kMaxTileCols] is a constant 0 word
 
 struct SliceDesc {
     uint32_t off;           // element offset of the slice / kStepElems

@@ -85,7 +85,7 @@ def test_fixed_edge_cases(gpu, port):
     y, want, _ = run_fixed_csr(port, (128, 64, ip, np.zeros(0, np.uint32), np.zeros(0, np.float32)),
                                np.ones(64, np.float32))
     assert np.array_equal(y, want) and not y.any()
-    n = 50000
+    n = 70000
     ip = np.array([0, 0, n, n, n + 1], np.uint32)
     ix = np.concatenate([np.arange(n), [3]]).astype(np.uint32)
     d = np.full(n + 1, 0.001, np.float32)
