@@ -87,6 +87,7 @@ def lib():
     L.hsb_spmv.argtypes = [vp]
     L.hsb_sync.argtypes = [vp]
     L.hsb_download_result.argtypes = [vp, vp, C.c_uint]
+    L.hsb_download_result_async.argtypes = [vp, vp, C.c_uint]
     L.hsb_top_wrapper.argtypes = [C.c_int, C.POINTER(vp), vp, vp] + [C.c_uint] * 5
     L.hsb_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.hsb_set_replicas.argtypes = [vp, C.c_int]
@@ -210,6 +211,10 @@ class Context:
         if out is None:
             out = np.empty(self.rows, dtype)
         _check(lib().hsb_download_result(self.h, _ptr(out), out.size))
+        return out
+
+    def download_result_async(self, out):
+        _check(lib().hsb_download_result_async(self.h, _ptr(out), out.size))
         return out
 
     def stats(self):

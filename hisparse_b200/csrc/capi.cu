@@ -64,9 +64,17 @@ struct hsb_ctx {
     uint32_t *d_cta_seg = nullptr;        // [slots][sm_count + 1]
     hsb::Segment *d_segs = nullptr;
     std::vector<uint32_t> plan_grid;      // CTAs used by each of those launches
+    uint32_t smem_bytes = 0;              // dynamic shared memory a launch needs: widest x tile + the zero words
     // vectors
-    uint32_t *d_x = nullptr;              // x_words words (padded to whole tiles, zero filled)
+    // x is double buffered so that the upload of the next vector (copy stream) overlaps the SpMV that
+    // still reads the current one; x_words words each (padded to whole tiles, zero filled)
+    uint32_t *d_x[2] = {nullptr, nullptr};
+    int x_latest = 0;                     // buffer the next launch reads
+    bool x_dirty = false;                 // uploaded since the last launch: the launch must wait for the copy
     uint32_t *d_y = nullptr;              // rows words
+    bool y_busy = false;                  // an asynchronous download of d_y may still be running
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_xready = nullptr, ev_xfree[2] = {nullptr, nullptr}, ev_yready = nullptr, ev_ydone = nullptr;
     // rows + 1 accumulators (uint64 fixed / fp32 float) x 2: a launch adds into one buffer while it
     // drains the other (the previous launch's sums) into y
     void *d_acc[2] = {nullptr, nullptr};
@@ -83,8 +91,8 @@ namespace {
 void free_matrix(hsb_ctx *c) {
     for (auto &m : c->mats) m.release();
     c->mats.clear();
-    cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_acc[0]); cudaFree(c->d_acc[1]); cudaFree(c->d_cta_seg); cudaFree(c->d_segs);
-    c->d_x = nullptr; c->d_y = nullptr; c->d_acc[0] = c->d_acc[1] = nullptr; c->d_cta_seg = nullptr; c->d_segs = nullptr;
+    cudaFree(c->d_x[0]); cudaFree(c->d_x[1]); cudaFree(c->d_y); cudaFree(c->d_acc[0]); cudaFree(c->d_acc[1]); cudaFree(c->d_cta_seg); cudaFree(c->d_segs);
+    c->d_x[0] = c->d_x[1] = nullptr; c->d_y = nullptr; c->x_latest = 0; c->x_dirty = false; c->y_busy = false; c->d_acc[0] = c->d_acc[1] = nullptr; c->d_cta_seg = nullptr; c->d_segs = nullptr;
     c->drain_pending = false; c->acc_cur = 0;
     c->have_matrix = false;
 }
@@ -135,8 +143,11 @@ int upload_tiled(hsb_ctx *c, const hsb::TiledMatrix &M) {
     CUDA_TRY(cudaMemcpyAsync(c->d_segs, segs.data(), segs.size() * sizeof(hsb::Segment), cudaMemcpyHostToDevice, c->stream));
     // x is padded to whole tiles so that every bulk copy of a tile stays inside the buffer
     c->x_words = M.n_col_tiles * M.tile_cols;
-    CUDA_TRY(cudaMalloc(&c->d_x, (size_t)c->x_words * 4 + 16));
-    CUDA_TRY(cudaMemsetAsync(c->d_x, 0, (size_t)c->x_words * 4, c->stream));
+    for (int b = 0; b < 2; b++) {
+        CUDA_TRY(cudaMalloc(&c->d_x[b], (size_t)c->x_words * 4 + 16));
+        CUDA_TRY(cudaMemsetAsync(c->d_x[b], 0, (size_t)c->x_words * 4, c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev_xfree[b], c->stream));
+    }
     CUDA_TRY(cudaMalloc(&c->d_y, (size_t)std::max(c->rows, 1u) * 4));
     CUDA_TRY(cudaMemsetAsync(c->d_y, 0, (size_t)std::max(c->rows, 1u) * 4, c->stream));
     const size_t esz = c->arith == hsb::kArithFixed ? 8 : 4;
@@ -146,6 +157,9 @@ int upload_tiled(hsb_ctx *c, const hsb::TiledMatrix &M) {
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->grid = (int)c->plan_grid[0];
+    uint32_t widest = 8;
+    for (const auto &td : M.tiles) widest = std::max(widest, td.col_count);
+    c->smem_bytes = widest * 4u + hsb::kXTileOffset;
     c->next_replica = 0;
     c->have_matrix = true;
     return HSB_OK;
@@ -161,14 +175,22 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
     p.vals = m.vals; p.cols = m.cols; p.slice_rows = m.slice_rows;
     p.cta_seg = c->d_cta_seg + slot * (size_t)(G + 1);
     p.segs = c->d_segs;
-    p.x = c->d_x; p.y = c->d_y;
+    if (c->x_dirty) {                                   // the vector this launch reads is still being uploaded
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_xready, 0));
+        c->x_dirty = false;
+    }
+    if (c->drain_pending && c->y_busy) {                // the prologue drain writes y: wait for its last reader
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_ydone, 0));
+        c->y_busy = false;
+    }
+    p.x = c->d_x[c->x_latest]; p.y = c->d_y;
     p.acc = c->d_acc[c->acc_cur];
     p.drain_acc = c->drain_pending ? c->d_acc[c->acc_cur ^ 1] : nullptr;
     p.drain_begin = c->drain_begin; p.drain_end = c->drain_end;
     p.trash_row = c->rows;
     p.trace = c->d_trace;
     if (k0) CUDA_TRY(cudaEventRecord(k0, c->stream));
-    CUDA_TRY(hsb::launch_spmv(c->arith, p, grid, c->stream));
+    CUDA_TRY(hsb::launch_spmv(c->arith, p, grid, c->smem_bytes, c->stream));
     c->launches++;
     if (k1) CUDA_TRY(cudaEventRecord(k1, c->stream));
     c->drain_pending = true;
@@ -180,6 +202,10 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
 // make y final: drain what the last launch accumulated (stream-ordered, no host sync)
 int finish(hsb_ctx *c) {
     if (!c->drain_pending) return HSB_OK;
+    if (c->y_busy) {
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_ydone, 0));
+        c->y_busy = false;
+    }
     CUDA_TRY(hsb::launch_drain(c->arith, c->d_acc[c->acc_cur ^ 1], c->d_y, c->drain_begin, c->drain_end, c->rows,
                                c->stream));
     c->launches++;
@@ -237,7 +263,12 @@ hsb_ctx *hsb_create(int device, int impl) {
         return nullptr;
     }
     c->sm_count = prop.multiProcessorCount;
-    e = hsb::configure_kernels();
+    e = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
+    cudaEvent_t *evs[] = {&c->ev_xready, &c->ev_xfree[0], &c->ev_xfree[1], &c->ev_yready, &c->ev_ydone};
+    for (cudaEvent_t *ev : evs)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = hsb::configure_kernels();
     if (e != cudaSuccess) {
         set_err(HSB_ECUDA, std::string("kernel configuration failed: ") + cudaGetErrorString(e));
         cudaStreamDestroy(c->stream);
@@ -251,8 +282,14 @@ void hsb_destroy(hsb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->s_h2d);
+    cudaStreamSynchronize(c->s_d2h);
     free_matrix(c);
     cudaFree(c->d_trace);
+    cudaEvent_t evs[] = {c->ev_xready, c->ev_xfree[0], c->ev_xfree[1], c->ev_yready, c->ev_ydone};
+    for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->s_h2d);
+    cudaStreamDestroy(c->s_d2h);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -309,7 +346,15 @@ int hsb_upload_vector(hsb_ctx *c, const void *x_packed, unsigned num_cols) {
     if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
     if (num_cols > c->x_words || num_cols < c->cols) return set_err(HSB_EINVAL, "num_cols does not match the matrix");
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaMemcpyAsync(c->d_x, x_packed, (size_t)num_cols * 4, cudaMemcpyHostToDevice, c->stream));
+    // write the buffer no in-flight launch reads: its last readers were launched before the previous
+    // upload, which is when ev_xfree[b] was recorded on the compute stream
+    const int b = c->x_latest ^ 1;
+    CUDA_TRY(cudaStreamWaitEvent(c->s_h2d, c->ev_xfree[b], 0));
+    CUDA_TRY(cudaMemcpyAsync(c->d_x[b], x_packed, (size_t)num_cols * 4, cudaMemcpyHostToDevice, c->s_h2d));
+    CUDA_TRY(cudaEventRecord(c->ev_xready, c->s_h2d));
+    CUDA_TRY(cudaEventRecord(c->ev_xfree[c->x_latest], c->stream));   // "every launch so far that reads the old buffer"
+    c->x_latest = b;
+    c->x_dirty = true;
     return HSB_OK;
 }
 
@@ -339,18 +384,32 @@ int hsb_sync(hsb_ctx *c) {
     if (!c) return set_err(HSB_EINVAL, "null context");
     CUDA_TRY(cudaSetDevice(c->device));
     if (c->have_matrix) { int rc = finish(c); if (rc) return rc; }
+    CUDA_TRY(cudaStreamSynchronize(c->s_h2d));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
+    c->y_busy = false;
     return HSB_OK;
 }
 
-int hsb_download_result(hsb_ctx *c, void *y_packed, unsigned num_rows) {
+int hsb_download_result_async(hsb_ctx *c, void *y_packed, unsigned num_rows) {
     if (!c || !y_packed) return set_err(HSB_EINVAL, "null argument");
     if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
     if (num_rows > c->rows) return set_err(HSB_EINVAL, "num_rows exceeds the matrix");
     CUDA_TRY(cudaSetDevice(c->device));
     { int rc = finish(c); if (rc) return rc; }
-    CUDA_TRY(cudaMemcpyAsync(y_packed, c->d_y, (size_t)num_rows * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev_yready, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->ev_yready, 0));
+    CUDA_TRY(cudaMemcpyAsync(y_packed, c->d_y, (size_t)num_rows * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    CUDA_TRY(cudaEventRecord(c->ev_ydone, c->s_d2h));
+    c->y_busy = true;
+    return HSB_OK;
+}
+
+int hsb_download_result(hsb_ctx *c, void *y_packed, unsigned num_rows) {
+    int rc = hsb_download_result_async(c, y_packed, num_rows);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
+    c->y_busy = false;
     return HSB_OK;
 }
 
@@ -477,7 +536,7 @@ int hsb_debug_trace(hsb_ctx *c, unsigned long long *out, size_t capacity) {
     return (int)n;
 }
 
-void *hsb_device_x(hsb_ctx *c) { return c ? c->d_x : nullptr; }
+void *hsb_device_x(hsb_ctx *c) { return c ? c->d_x[c->x_latest] : nullptr; }
 void *hsb_device_y(hsb_ctx *c) { return c ? c->d_y : nullptr; }
 void *hsb_stream(hsb_ctx *c) { return c ? (void *)c->stream : nullptr; }
 

@@ -77,13 +77,15 @@ int hsb_format_expand(const hsb_format *f, uint32_t *indptr, uint32_t *indices, 
                             continue;
                         }
                         if (ended || row >= M.rows || row < row_lo) return HSB_EINVAL;
-                        if (c16 >= td.col_count || td.col_base + c16 >= M.cols) return HSB_EINVAL;
+                        if (c16 < hsb::kColBias) return HSB_EINVAL;
+                        const uint32_t lc = c16 - hsb::kColBias;
+                        if (lc >= td.col_count || td.col_base + lc >= M.cols) return HSB_EINVAL;
                         len++;
                         if (pass == 0) {
                             indptr[row + 1]++;
                         } else {
                             uint32_t at = cursor[row]++;
-                            indices[at] = td.col_base + c16;
+                            indices[at] = td.col_base + lc;
                             vals[at] = M.vals[e];
                         }
                     }

@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_tiles_kernel(const SpmvParam
     if (g0 < g1) {
         if (tid == 0) {
             mbar_init(&bar, 1);
-            xs[kPadCol] = 0u;                                     // what padding slots multiply by
         }
+        if (tid < kColBias) xs[tid] = 0u;                         // what padding slots multiply by
         __syncthreads();
         uint32_t parity = 0;
         for (uint32_t g = g0; g < g1; g++) {
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_tiles_kernel(const SpmvParam
                 mbar_arrive_expect_tx(&bar, bytes);
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(p.x + h0.w);
                 for (uint32_t off = 0; off < bytes; off += kBulkPiece)
-                    bulk_g2s(smem_raw + off, src + off, min(kBulkPiece, bytes - off), &bar);
+                    bulk_g2s(smem_raw + kXTileOffset + off, src + off, min(kBulkPiece, bytes - off), &bar);
             }
             // this warp's equal-cost share of the segment (host plan)
             const uint32_t ta = __ldg(&sg->warp_t[warp]), tb = __ldg(&sg->warp_t[warp + 1]);
@@ -292,11 +292,11 @@ cudaError_t configure_kernels() {
                                 (int)kSmemBytes);
 }
 
-cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, cudaStream_t stream) {
+cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, uint32_t smem_bytes, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see griddepcontrol.wait in the kernel

@@ -42,7 +42,8 @@ namespace hsb {
 constexpr int kThreads = 1024;                       // 32 warps: one CTA per SM
 constexpr int kWarps = kThreads / 32;
 constexpr uint32_t kXTileBytes = kMaxTileCols * 4;   // 224 KB
-constexpr uint32_t kSmemBytes = kXTileBytes + 16;    // + the constant-zero word padding slots gather
+constexpr uint32_t kXTileOffset = kColBias * 4;      // xs[0..7] = 0: what padding slots (column id 0) gather
+constexpr uint32_t kSmemBytes = kXTileBytes + kXTileOffset;   // upper bound; a launch asks for what its tiles need
 constexpr uint32_t kBulkPiece = 16384;               // bytes per cp.async.bulk
 constexpr int kPrefetch = 4;                         // slice steps in flight per warp
 
@@ -64,7 +65,7 @@ struct SpmvParams {
 
 enum { kArithFixed = 0, kArithFloat = 1 };
 
-cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, cudaStream_t stream);
+cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, uint32_t smem_bytes, cudaStream_t stream);
 // drain only: y[r] = clamp(acc[r]), acc[r] = 0 for r in [row_begin, row_end) and the trash slot
 cudaError_t launch_drain(int arith, void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end,
                          uint32_t trash_row, cudaStream_t stream);

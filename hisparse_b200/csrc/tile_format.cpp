@@ -157,7 +157,7 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
                 uint32_t col = indices[e], t = col / tile_cols;
                 uint64_t p = cur[t]++;
                 a_vals[p] = vals[e];
-                a_cols[p] = (uint16_t)(col - t * tile_cols);
+                a_cols[p] = (uint16_t)(col - t * tile_cols + kColBias);
                 if (in_row[t]++ == 0) touched.push_back(t);
             }
             for (uint32_t t : touched) {

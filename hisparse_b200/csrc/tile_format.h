@@ -38,7 +38,8 @@ constexpr int kSlotBlock = 4;                            // non-zeros per lane p
 constexpr int kStepElems = kLanes * kSlotBlock;          // 128 elements per slice step
 constexpr uint32_t kMaxStreamLen = 128;                  // non-zeros per lane stream (keeps 32-bit partial sums exact)
 constexpr uint32_t kMaxTileCols = 57344;                 // 224 KB of x in shared memory (of 227 KB per CTA), 16-bit ids
-constexpr uint16_t kPadCol = 57344;                      // column id of padding slots: xs[kMaxTileCols] is a constant 0 word
+constexpr uint16_t kColBias = 8;                         // stored column id = tile-local column + 8 ...
+constexpr uint16_t kPadCol = 0;                          // ... so that id 0 (padding slots) can point at a constant 0 word
 
 struct SliceDesc {
     uint32_t off;           // element offset of the slice / kStepElems

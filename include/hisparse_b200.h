@@ -96,7 +96,8 @@ int hsb_upload_matrix_cpsr(hsb_ctx *ctx, const void *const ch[HSB_NUM_HBM_CHANNE
 int hsb_upload_matrix_csr(hsb_ctx *ctx, uint32_t rows, uint32_t cols, const uint32_t *indptr,
                           const uint32_t *indices, const void *vals, uint32_t rows_per_partition);
 
-/* == vector_buf on HBM[20] + migrate (sw/host.cpp:282-298). x_packed: num_cols 32-bit words. */
+/* == vector_buf on HBM[20] + migrate (sw/host.cpp:282-298). x_packed: num_cols 32-bit words.
+ * Asynchronous on a copy stream; the next hsb_spmv* waits for it. */
 int hsb_upload_vector(hsb_ctx *ctx, const void *x_packed, unsigned num_cols);
 
 /* == setArg(row_part_id, part_len) + enqueueTask x5 + finish for ONE row partition
@@ -115,6 +116,10 @@ int hsb_sync(hsb_ctx *ctx);
 /* == enqueueMigrateMemObjects(result_buf -> host) + finish (sw/host.cpp:370-371).
  * y_packed: num_rows 32-bit words, natural row order. Synchronises. */
 int hsb_download_result(hsb_ctx *ctx, void *y_packed, unsigned num_rows);
+/* The same without the finish(): the copy runs on its own stream (the reference's queue is out of
+ * order too, sw/host.cpp:586-590); y_packed is valid after the next hsb_sync(). Together with the
+ * double-buffered x of hsb_upload_vector this lets upload(k+1), SpMV(k) and download(k-1) overlap. */
+int hsb_download_result_async(hsb_ctx *ctx, void *y_packed, unsigned num_rows);
 
 /* == spmv_csim/csim.cpp:22-46 `top_wrapper`: one row partition, host buffers in, host buffer out.
  * Channel image lengths are recovered from the image headers. Uploads, runs, downloads. */

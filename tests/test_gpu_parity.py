@@ -90,7 +90,7 @@ def test_fixed_edge_cases(gpu, port):
     ix = np.concatenate([np.arange(n), [3]]).astype(np.uint32)
     d = np.full(n + 1, 0.001, np.float32)
     y, want, st = run_fixed_csr(port, (4, n, ip, ix, d), np.full(n, 0.5, np.float32))
-    assert np.array_equal(y, want) and st["n_col_tiles"] == 2
+    assert np.array_equal(y, want) and st["n_col_tiles"] == 3     # 70000 columns: three tiles of <= 32768
     y, want, _ = run_fixed_csr(port, (4, n, ip, ix, d), np.zeros(n, np.float32))
     assert np.array_equal(y, want) and not y.any()
     # reference-style x in {0,1} (sw/host.cpp:238)
@@ -113,6 +113,33 @@ def test_repeated_runs_and_vector_update(gpu, port):
         ctx.spmv()
         assert np.array_equal(ctx.download_result(), port.spmv_q824(indptr, indices, words, xw)), it
     assert ctx.stats()["kernel_launches"] == 10      # per SpMV: one fused launch + the drain forced by the download
+    ctx.close()
+
+
+def test_pipelined_upload_spmv_download(gpu, port):
+    """upload(k+1) / SpMV(k) / download(k-1) overlap on three streams: every result still exact."""
+    rows, cols, indptr, indices, data = matgen.rmat_csr(30000, 900000, 23)
+    words = port.quantize(data)
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    ctx.upload_matrix_csr(rows, cols, indptr, indices, words)
+    rng = np.random.default_rng(8)
+    n = 12
+    xs = [capi.PinnedArray(cols) for _ in range(n)]
+    ys = [capi.PinnedArray(rows) for _ in range(n)]
+    for k in range(n):
+        xs[k].array[:] = port.quantize(rng.random(cols, dtype=np.float32))
+    for k in range(n):
+        ctx.upload_vector(xs[k].array)
+        ctx.spmv()
+        ctx.download_result_async(ys[k].array)
+    ctx.sync()
+    for k in range(n):
+        assert np.array_equal(ys[k].array, port.spmv_q824(indptr, indices, words, xs[k].array)), k
+    # several SpMVs on one vector, then a new vector without an intervening download
+    ctx.spmv(); ctx.spmv()
+    ctx.upload_vector(xs[3].array)
+    ctx.spmv()
+    assert np.array_equal(ctx.download_result(), port.spmv_q824(indptr, indices, words, xs[3].array))
     ctx.close()
 
 

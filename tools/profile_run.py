@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--impl", default="fixed")
     ap.add_argument("--config", default="c2")
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--replicas", type=int, default=0)
     a = ap.parse_args()
     rows, cols, indptr, indices, data = make(a.config)
     r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
@@ -38,7 +39,7 @@ def main():
     ctx = capi.Context(0, a.impl)
     ctx.upload_matrix_csr(r2, c2, ip2, indices, data)
     st = ctx.stats()
-    ctx.set_replicas(max(2, int(np.ceil(2.5 * 126 * 2 ** 20 / max(st["format_bytes"], 1)))))
+    ctx.set_replicas(a.replicas or max(2, int(np.ceil(2.5 * 126 * 2 ** 20 / max(st["format_bytes"], 1)))))
     ctx.upload_vector(x)
     if a.time:
         step, kern = ctx.time_spmv(20, 400)
