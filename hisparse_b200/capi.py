@@ -96,6 +96,7 @@ def lib():
         getattr(L, n).argtypes = [vp]
         getattr(L, n).restype = vp
     L.hsb_debug_trace.argtypes = [vp, vp, sz]
+    L.hsb_debug_plan.argtypes = [vp, vp, vp, sz]
     L.hsb_format_build.argtypes = [u32, u32, vp, vp, vp, u32, u32]
     L.hsb_format_build.restype = vp
     L.hsb_format_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -240,6 +241,14 @@ class Context:
         if rc < 0:
             _check(rc)
         return out.reshape(-1, 34)
+
+    def plan(self):
+        n = self.stats()["sm_count"]
+        a, b = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        rc = lib().hsb_debug_plan(self.h, _ptr(a), _ptr(b), n)
+        if rc < 0:
+            _check(rc)
+        return a[:rc], b[:rc]
 
     def device_x(self):
         return lib().hsb_device_x(self.h)

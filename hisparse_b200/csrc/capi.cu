@@ -64,6 +64,7 @@ struct hsb_ctx {
     uint32_t *d_cta_seg = nullptr;        // [slots][sm_count + 1]
     hsb::Segment *d_segs = nullptr;
     std::vector<uint32_t> plan_grid;      // CTAs used by each of those launches
+    std::vector<uint32_t> plan_steps, plan_slices;   // slot 0: steps / slices started per CTA (profiling aid)
     uint32_t smem_bytes = 0;              // dynamic shared memory a launch needs: widest x tile + the zero words
     // vectors
     // x is double buffered so that the upload of the next vector (copy stream) overlaps the SpMV that
@@ -136,6 +137,16 @@ int upload_tiled(hsb_ctx *c, const hsb::TiledMatrix &M) {
         cta_seg_all.insert(cta_seg_all.end(), cs.begin(), cs.end());
     };
     plan(0, 0, M.n_row_parts * T);
+    c->plan_steps.assign(G, 0); c->plan_slices.assign(G, 0);
+    for (uint32_t b = 0; b < G; b++)
+        for (uint32_t g = cta_seg_all[b]; g < cta_seg_all[b + 1]; g++) {
+            c->plan_steps[b] += segs[g].t_hi - segs[g].t_lo;
+            const hsb::TileDesc &td = M.tiles[segs[g].tile];
+            for (uint32_t s = td.slice_begin; s < td.slice_end; s++) {
+                uint32_t o = M.slices[s].off - td.step_begin;
+                if (o >= segs[g].t_lo && o < segs[g].t_hi) c->plan_slices[b]++;
+            }
+        }
     for (uint32_t j = 0; j < M.n_row_parts; j++) plan(1 + j, j * T, (j + 1) * T);
     CUDA_TRY(cudaMalloc(&c->d_cta_seg, cta_seg_all.size() * 4));
     CUDA_TRY(cudaMemcpyAsync(c->d_cta_seg, cta_seg_all.data(), cta_seg_all.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -534,6 +545,13 @@ int hsb_debug_trace(hsb_ctx *c, unsigned long long *out, size_t capacity) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaMemcpy(out, c->d_trace, n * 8, cudaMemcpyDeviceToHost));
     return (int)n;
+}
+
+int hsb_debug_plan(hsb_ctx *c, uint32_t *steps, uint32_t *slices, size_t capacity) {
+    if (!c || !c->have_matrix || capacity < c->plan_steps.size()) return set_err(HSB_EINVAL, "bad argument");
+    std::memcpy(steps, c->plan_steps.data(), c->plan_steps.size() * 4);
+    std::memcpy(slices, c->plan_slices.data(), c->plan_slices.size() * 4);
+    return (int)c->plan_steps.size();
 }
 
 void *hsb_device_x(hsb_ctx *c) { return c ? c->d_x[c->x_latest] : nullptr; }

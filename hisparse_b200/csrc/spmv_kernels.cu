@@ -2,6 +2,7 @@
 #include "spmv_kernels.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace hsb {
 namespace {
@@ -104,12 +105,31 @@ struct FloatArith {                                   // fp32 multiply, then fp3
     }
 };
 
+// The CTA's dynamic shared memory: xs[0..7] = 0 (padding slots), xs[8 + c] = x[tile column c].
+extern __shared__ __align__(128) uint32_t xs[];
+
+// Gather of the vecbuf_reader step: x word of the low / high 16-bit column id packed in `c`.
+// Written in PTX so that each address costs two ALU instructions (mask or shift, then one
+// shift-add onto the shared base held in a register) instead of the three nvcc emits for xs[id].
+__device__ __forceinline__ uint32_t gather_lo(uint32_t xs_base, uint32_t c) {
+    uint32_t v;
+    asm("{\n\t.reg .u32 t;\n\tand.b32 t, %1, 0xFFFF;\n\tmad.lo.u32 t, t, 4, %2;\n\tld.shared.u32 %0, [t];\n\t}"
+        : "=r"(v) : "r"(c), "r"(xs_base));
+    return v;
+}
+__device__ __forceinline__ uint32_t gather_hi(uint32_t xs_base, uint32_t c) {
+    uint32_t v;
+    asm("{\n\t.reg .u32 t;\n\tshr.u32 t, %1, 16;\n\tmad.lo.u32 t, t, 4, %2;\n\tld.shared.u32 %0, [t];\n\t}"
+        : "=r"(v) : "r"(c), "r"(xs_base));
+    return v;
+}
+
 template <class A>
-__device__ __forceinline__ void mac4(A &acc, const uint32_t *xs, const uint4 &v, const uint2 &c) {
-    acc.mac(v.x, xs[c.x & 0xFFFFu]);
-    acc.mac(v.y, xs[c.x >> 16]);
-    acc.mac(v.z, xs[c.y & 0xFFFFu]);
-    acc.mac(v.w, xs[c.y >> 16]);
+__device__ __forceinline__ void mac4(A &acc, uint32_t xs_base, const uint4 &v, const uint2 &c) {
+    acc.mac(v.x, gather_lo(xs_base, c.x));
+    acc.mac(v.y, gather_hi(xs_base, c.x));
+    acc.mac(v.z, gather_lo(xs_base, c.y));
+    acc.mac(v.w, gather_hi(xs_base, c.y));
 }
 
 // Slice geometry of a tile from its 32-entry table (lane c holds cnt_ge[c], see TileDesc):
@@ -124,7 +144,7 @@ __device__ __forceinline__ uint32_t steps_of(uint32_t cnt, uint32_t i) {
 // columns) steps that may start and end inside a slice. Lanes own lane streams; whenever a slice
 // (or the run) ends, the lane's partial sum is added to its row and the accumulator restarts.
 template <class A, class F>
-__device__ __forceinline__ void stream_steps(const SpmvParams &p, const uint32_t *xs, uint64_t *bar, uint32_t parity,
+__device__ __forceinline__ void stream_steps(const SpmvParams &p, uint64_t *bar, uint32_t parity,
                                              uint32_t cnt, uint32_t slice_begin, uint32_t n_slices,
                                              uint32_t step_begin, uint32_t ta, uint32_t tb, uint32_t first_slice,
                                              uint32_t lane, bool first_segment, F &before_x_wait) {
@@ -159,6 +179,8 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, const uint32_t
     mbar_wait(bar, parity);
     if (!remaining) return;
 
+    uint32_t xs_base = smem_u32(xs);
+    asm volatile("" : "+r"(xs_base));                        // keep it in a register: no per-step rematerialisation
     A acc;
     acc.clear();
     // Row update of a finished slice. Streams of one row sit in adjacent lanes (stable sort), and
@@ -188,7 +210,7 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, const uint32_t
     while (remaining >= (uint32_t)kPrefetch) {
 #pragma unroll
         for (int j = 0; j < kPrefetch; j++) {
-            mac4(acc, xs, vb[j], cb[j]);
+            mac4(acc, xs_base, vb[j], cb[j]);
             if (remaining > (uint32_t)(kPrefetch + j)) {     // step (consumed + kPrefetch + j) exists
                 vb[j] = ldg_stream128(vp + j * kLanes);
                 cb[j] = ldg_stream64(cp + j * kLanes);
@@ -202,7 +224,7 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, const uint32_t
 #pragma unroll
     for (int j = 0; j < kPrefetch - 1; j++)
         if ((uint32_t)j < remaining) {
-            mac4(acc, xs, vb[j], cb[j]);
+            mac4(acc, xs_base, vb[j], cb[j]);
             step_done();
         }
     // the run ended inside a slice: hand over what has been accumulated so far
@@ -211,8 +233,7 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, const uint32_t
 
 template <class A>
 __global__ void __launch_bounds__(kThreads, 1) spmv_tiles_kernel(const SpmvParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t *xs = reinterpret_cast<uint32_t *>(smem_raw);
+    unsigned char *smem_raw = reinterpret_cast<unsigned char *>(xs);
     __shared__ __align__(8) uint64_t bar;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -263,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_tiles_kernel(const SpmvParam
             // this warp's equal-cost share of the segment (host plan)
             const uint32_t ta = __ldg(&sg->warp_t[warp]), tb = __ldg(&sg->warp_t[warp + 1]);
             const uint32_t first_slice = __ldg(&sg->warp_slice[warp]);
-            stream_steps<A>(p, xs, &bar, parity, cnt, h1.y, h1.z, h1.w, ta, tb, first_slice, lane, g == g0,
+            stream_steps<A>(p, &bar, parity, cnt, h1.y, h1.z, h1.w, ta, tb, first_slice, lane, g == g0,
                             wait_for_previous_launch);
             parity ^= 1u;
             if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * (kWarps + 2) + warp] = clock64() - t_start;
@@ -298,11 +319,12 @@ cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, uint32_t smem_
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
+    static const bool pdl = std::getenv("HSB_NO_PDL") == nullptr;       // tracing aid: serialise launches
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see griddepcontrol.wait in the kernel
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl ? 1 : 0;
     if (arith == kArithFixed) return cudaLaunchKernelEx(&cfg, spmv_tiles_kernel<FixedArith>, p);
     return cudaLaunchKernelEx(&cfg, spmv_tiles_kernel<FloatArith>, p);
 }

@@ -106,3 +106,13 @@ def pad_csr(rows, cols, indptr, row_div, col_div):
     c2 = cols + (-cols) % col_div
     ip = np.concatenate([indptr, np.full(r2 - rows, indptr[-1], np.uint32)]).astype(np.uint32)
     return r2, c2, ip
+
+
+def quantize_q824(v):
+    """float -> raw Q8.24 words the way the host conversion does it (spmv::ufixed_q8_24 in
+    hisparse_b200/host/fixed_point.h == csr_matrix_convert_from_float<VAL_T>, sw/data_loader.h:76-84):
+    round half up at 2^-24, clamp to [0, 2^32 - 1]; negatives and NaN give 0."""
+    d = np.asarray(v, dtype=np.float64)
+    s = np.floor(np.ldexp(d, 24) + 0.5)
+    s = np.where(d > 0, s, 0.0)
+    return np.minimum(s, 4294967295.0).astype(np.uint32)

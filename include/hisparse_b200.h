@@ -141,6 +141,8 @@ int hsb_time_spmv(hsb_ctx *ctx, int warmup, int steps, float *step_ms, float *ke
  * then CTA "arrived at the grid barrier", then "drain done". out == NULL arms (capacity != 0) or
  * disarms (capacity == 0) the trace and returns the number of words. */
 int hsb_debug_trace(hsb_ctx *ctx, unsigned long long *out, size_t capacity);
+/* Profiling aid: steps and slices the whole-matrix plan gives to every CTA. */
+int hsb_debug_plan(hsb_ctx *ctx, uint32_t *steps, uint32_t *slices, size_t capacity);
 /* raw device pointers / stream for callers that move x or y with NCCL (torch.distributed);
  * call hsb_sync() before reading device y */
 void *hsb_device_x(hsb_ctx *ctx);

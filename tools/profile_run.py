@@ -34,8 +34,7 @@ def main():
     x = np.zeros(c2, np.float32)
     x[:cols] = np.random.default_rng(1).random(cols, dtype=np.float32)
     if a.impl == "fixed":
-        port = hsoracle.Port()
-        data, x = port.quantize(data * np.float32(0.05)), port.quantize(x)
+        data, x = matgen.quantize_q824(data * np.float32(0.05)), matgen.quantize_q824(x)
     ctx = capi.Context(0, a.impl)
     ctx.upload_matrix_csr(r2, c2, ip2, indices, data)
     st = ctx.stats()
