@@ -13,7 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libhisparse_b200.so")
+LIB_PATH = os.environ.get("HSB_LIB") or os.path.join(HERE, "libhisparse_b200.so")   # HSB_LIB: tuning builds
 HEADER = os.path.join(ROOT, "include", "hisparse_b200.h")
 
 IMPL_FIXED, IMPL_FLOAT_POB, IMPL_FLOAT_STALL = 0, 1, 2
@@ -240,7 +240,7 @@ class Context:
         rc = lib().hsb_debug_trace(self.h, _ptr(out), n)
         if rc < 0:
             _check(rc)
-        return out.reshape(-1, 34)
+        return out.reshape(self.stats()["sm_count"], -1)
 
     def plan(self):
         n = self.stats()["sm_count"]

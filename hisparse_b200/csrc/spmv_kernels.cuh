@@ -39,13 +39,16 @@
 
 namespace hsb {
 
-constexpr int kThreads = 1024;                       // 32 warps: one CTA per SM
-constexpr int kWarps = kThreads / 32;
+constexpr int kWarps = kWarpsPerCta;                 // one CTA per SM
+constexpr int kThreads = kWarps * 32;
 constexpr uint32_t kXTileBytes = kMaxTileCols * 4;   // 224 KB
 constexpr uint32_t kXTileOffset = kColBias * 4;      // xs[0..7] = 0: what padding slots (column id 0) gather
 constexpr uint32_t kSmemBytes = kXTileBytes + kXTileOffset;   // upper bound; a launch asks for what its tiles need
 constexpr uint32_t kBulkPiece = 16384;               // bytes per cp.async.bulk
-constexpr int kPrefetch = 4;                         // slice steps in flight per warp
+#ifndef HSB_PREFETCH
+#define HSB_PREFETCH 4
+#endif
+constexpr int kPrefetch = HSB_PREFETCH;              // slice steps in flight per warp
 
 struct SpmvParams {
     const uint32_t *vals;

@@ -372,11 +372,11 @@ Segment make_segment(const TiledMatrix &m, uint32_t tile, uint32_t t_lo, uint32_
     std::memcpy(g.cnt_ge, td.cnt_ge, sizeof g.cnt_ge);
     const double c0 = cost_at_step(m, td, t_lo), c1 = cost_at_step(m, td, t_hi);
     const uint32_t total = tile_steps_total(m, td);
-    for (int w = 0; w <= 32; w++) {
-        uint32_t t = w == 0 ? t_lo : (w == 32 ? t_hi : step_at_cost(m, td, c0 + (c1 - c0) * w / 32.0));
+    for (int w = 0; w <= kWarpsPerCta; w++) {
+        uint32_t t = w == 0 ? t_lo : (w == kWarpsPerCta ? t_hi : step_at_cost(m, td, c0 + (c1 - c0) * w / (double)kWarpsPerCta));
         t = std::min(std::max(t, w ? g.warp_t[w - 1] : t_lo), t_hi);
         g.warp_t[w] = t;
-        if (w < 32) g.warp_slice[w] = t < total ? slice_of_step_host(m, td, t) : g.n_slices;
+        if (w < kWarpsPerCta) g.warp_slice[w] = t < total ? slice_of_step_host(m, td, t) : g.n_slices;
     }
     return g;
 }

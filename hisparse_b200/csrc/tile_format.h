@@ -34,6 +34,10 @@
 namespace hsb {
 
 constexpr int kLanes = 32;
+#ifndef HSB_WARPS_PER_CTA
+#define HSB_WARPS_PER_CTA 32
+#endif
+constexpr int kWarpsPerCta = HSB_WARPS_PER_CTA;           // warps of the kernel's one CTA per SM (the planner cuts shares for them)
 constexpr int kSlotBlock = 4;                            // non-zeros per lane per load step
 constexpr int kStepElems = kLanes * kSlotBlock;          // 128 elements per slice step
 constexpr uint32_t kMaxStreamLen = 128;                  // non-zeros per lane stream (keeps 32-bit partial sums exact)

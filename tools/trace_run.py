@@ -20,7 +20,8 @@ for _ in range(5): ctx.spmv()
 ctx.sync(); ctx.trace(True)
 for _ in range(3): ctx.spmv()
 t = ctx.trace().astype(np.float64)
-w = t[:, :32]; arrive = t[:, 32]; done = t[:, 33]
+nw = t.shape[1] - 2
+w = t[:, :nw]; arrive = t[:, nw]; done = t[:, nw + 1]
 steps, slices = ctx.plan()
 print("per-CTA: steps slices | warp finish min / mean / max, CTA done  (SM cycles; run with HSB_NO_PDL=1)")
 for b in range(t.shape[0]):
