@@ -43,11 +43,26 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+WORKLOADS = {
+    # name: (description, impl, generator)            -- SURVEY.md section 8d; c2 is the bench line
+    "c1": ("C1: 4096x4096 uniform random, 1 %% density, fp32", "float_pob",
+           lambda m, r: m.random_csr(4096, 4096, 0.01, 0xC0FFEE01 + r)),
+    "c2": ("C2: googleplus-sized R-MAT 107614^2 (a,b,c=.57,.19,.19), fixed-point", "fixed",
+           lambda m, r: m.rmat_csr(N_NODES, NNZ_TARGET, SEED + r)),
+    "c3": ("C3: transformer-sized 512x33288 Bernoulli mask 50 %%, fp32 (float_pob)", "float_pob",
+           lambda m, r: m.bernoulli_csr(512, 33288, 0.5, 0xC0FFEE03 + r)),
+    "c4": ("C4: ogbl-ppa-sized symmetric R-MAT 576289^2, fp32", "float_pob",
+           lambda m, r: m.rmat_csr(576289, 42_460_000, 0xC0FFEE04 + r, symmetric=True, oversample=1.5)),
+}
+WORKLOAD = "c2"
+
+
 def workload(rank):
-    """C2 stand-in shard for `rank` (rank 0 == the single-GPU workload)."""
+    """Synthetic shard for `rank` (rank 0 == the single-GPU workload). Default: the C2 stand-in."""
     from hisparse_b200 import matgen
-    rows, cols, indptr, indices, data = matgen.rmat_csr(N_NODES, NNZ_TARGET, SEED + rank)
-    data = (data * np.float32(0.05)).astype(np.float32)      # keeps most row sums below saturation
+    rows, cols, indptr, indices, data = WORKLOADS[WORKLOAD][2](matgen, rank)
+    if WORKLOADS[WORKLOAD][1] == "fixed":
+        data = (data * np.float32(0.05)).astype(np.float32)  # keeps most row sums below saturation
     r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)  # util_round_csr_matrix_dim
     x = np.zeros(c2, np.float32)
     x[:cols] = np.random.default_rng(SEED).random(cols, dtype=np.float32)
@@ -172,7 +187,11 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="SpMVs per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
+                    help="c2 (default) is the bench line; the others are extra measurements")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.impl == "reference":
         return run_reference(args)
 
@@ -190,9 +209,13 @@ def main():
     r2, c2, ip2, indices, data, x = workload(rank)
     nnz = int(ip2[-1])
     from hisparse_b200 import matgen
-    words, xw = matgen.quantize_q824(data), matgen.quantize_q824(x)     # host-side float -> VAL_T conversion
+    impl = WORKLOADS[WORKLOAD][1]
+    if impl == "fixed":
+        words, xw = matgen.quantize_q824(data), matgen.quantize_q824(x)  # host-side float -> VAL_T conversion
+    else:
+        words, xw = data.view(np.uint32), x.view(np.uint32)
 
-    ctx = capi.Context(local, capi.IMPL_FIXED)
+    ctx = capi.Context(local, impl)
     ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
     st = ctx.stats()
     replicas = max(2, int(np.ceil(2.5 * L2_BYTES / max(st["format_bytes"], 1))))
@@ -289,22 +312,23 @@ def main():
         achieved = alg / (kernel_ms / 1e3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and WORKLOAD == "c2" and impl == "fixed":
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         out = {
             "metric": "SpMV GOPS (2*nnz/t, sw/benchmark.cpp:312-346)", "value": gops, "unit": "GOPS",
             "gbps": 8.0 * nnz_all / 2 ** 30 / sec_per_spmv,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "ms_per_spmv": 1e3 * sec_per_spmv, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 Q8.24 (ap_ufixed<32,8,AP_RND,AP_SAT>), 64-bit accumulate", "data": "synthetic",
-            "config": {"workload": "C2: googleplus-sized R-MAT 107614^2 (a,b,c=.57,.19,.19), nnz=%d per GPU, fixed-point" % nnz,
+            "dtype": "u32 Q8.24 (ap_ufixed<32,8,AP_RND,AP_SAT>), 64-bit accumulate" if impl == "fixed" else "f32",
+            "data": "synthetic",
+            "config": {"workload": (WORKLOADS[WORKLOAD][0] % ()) + ", nnz=%d per GPU" % nnz,
                        "spmv_per_step": B, "l2_policy": "inputs larger than L2: %d HBM replicas of the matrix "
                        "(%.0f MB each) used round-robin" % (replicas, st["format_bytes"] / 1e6),
                        "sharding": "row-block shard per GPU, x replicated (one NCCL broadcast before timing), "
                                    "no data-path collective" if world > 1 else "single GPU",
                        "tile_cols": st["tile_cols"], "col_tiles": st["n_col_tiles"], "grid": st["grid"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "spmv_tiles_kernel<FixedArith>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "spmv_tiles_kernel<%s>" % ("FixedArith" if impl == "fixed" else "FloatArith"),
                          "kernel_ms": kernel_ms, "kernel_ms_isolated": kernel_ms_isolated,
                          "algorithmic_bytes_per_launch": alg,
                          "format_bytes_per_launch": st["format_bytes"],
@@ -328,9 +352,16 @@ def main():
             out["cpu_baseline"] = cpu_baseline(r2, c2, ip2, indices, data, x, nnz)
             # the checker: the result words of this very run against the oracle's closed form
             from oracle import hsoracle
-            if not np.array_equal(y, hsoracle.Port().spmv_q824(ip2, indices, words, xw)):
+            port = hsoracle.Port()
+            if impl == "fixed":
+                ok = np.array_equal(y, port.spmv_q824(ip2, indices, words, xw))
+                out["config"]["parity"] = "bit-exact vs oracle checked in this run"
+            else:
+                y64, sa = port.spmv_f64(ip2, indices, data, x)
+                ok = bool(np.all(np.abs(y.view(np.float32).astype(np.float64) - y64) <= 1e-5 * sa + 1e-30))
+                out["config"]["parity"] = "within 1e-5 * sum|a_i x_i| of fp64 checked in this run"
+            if not ok:
                 raise SystemExit("bench: GPU result differs from the oracle -- refusing to report a number")
-            out["config"]["parity"] = "bit-exact vs oracle checked in this run"
         print(json.dumps(out))
     ctx.close()
     if dist is not None:

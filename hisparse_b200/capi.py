@@ -82,6 +82,8 @@ def lib():
     L.hsb_host_free.restype = None
     L.hsb_upload_matrix_cpsr.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.c_uint, C.c_uint, C.c_uint, C.c_uint]
     L.hsb_upload_matrix_csr.argtypes = [vp, u32, u32, vp, vp, vp, u32]
+    L.hsb_upload_matrix_csr_gpu.argtypes = [vp, u32, u32, vp, vp, vp, u32]
+    L.hsb_upload_matrix_csr_device.argtypes = [vp, u32, u32, C.c_uint64, vp, vp, vp, u32]
     L.hsb_upload_vector.argtypes = [vp, vp, C.c_uint]
     L.hsb_spmv_row_partition.argtypes = [vp] + [C.c_uint] * 5
     L.hsb_spmv.argtypes = [vp]
@@ -99,6 +101,8 @@ def lib():
     L.hsb_debug_plan.argtypes = [vp, vp, vp, sz]
     L.hsb_format_build.argtypes = [u32, u32, vp, vp, vp, u32, u32]
     L.hsb_format_build.restype = vp
+    L.hsb_format_from_context.argtypes = [vp]
+    L.hsb_format_from_context.restype = vp
     L.hsb_format_stats.argtypes = [vp, C.POINTER(Stats)]
     L.hsb_format_expand.argtypes = [vp, vp, vp, vp]
     L.hsb_format_free.argtypes = [vp]
@@ -183,11 +187,12 @@ class Context:
 
     __del__ = close
 
-    def upload_matrix_csr(self, rows, cols, indptr, indices, vals, rows_per_partition=0):
+    def upload_matrix_csr(self, rows, cols, indptr, indices, vals, rows_per_partition=0, on_gpu=False):
+        """on_gpu=True: the tile-stream format is built by device kernels (hsb_upload_matrix_csr_gpu)"""
         indptr, indices, vals = _words(indptr), _words(indices), _words(vals)
         assert indptr.size == rows + 1
-        _check(lib().hsb_upload_matrix_csr(self.h, rows, cols, _ptr(indptr), _ptr(indices), _ptr(vals),
-                                           rows_per_partition))
+        fn = lib().hsb_upload_matrix_csr_gpu if on_gpu else lib().hsb_upload_matrix_csr
+        _check(fn(self.h, rows, cols, _ptr(indptr), _ptr(indices), _ptr(vals), rows_per_partition))
         self.rows, self.cols = rows, cols
 
     def upload_matrix_cpsr(self, images, n_row_parts, n_col_parts, rows, cols):
@@ -272,6 +277,17 @@ def top_wrapper(impl, images, x, y, row_part_id, part_len, ncp, nparts, num_cols
 
 class Format:
     """Host-side view of the tile-stream format (no GPU)."""
+
+    @classmethod
+    def from_context(cls, ctx):
+        """the matrix resident on the device, downloaded for inspection"""
+        self = cls.__new__(cls)
+        self.h = lib().hsb_format_from_context(ctx.h)
+        if not self.h:
+            raise HsbError("hsb_format_from_context: " + lib().hsb_last_error().decode())
+        st = self.stats()
+        self.rows, self.nnz = st["rows"], st["nnz"]
+        return self
 
     def __init__(self, rows, cols, indptr, indices, vals, rows_per_partition=0, tile_cols=0):
         indptr, indices, vals = _words(indptr), _words(indices), _words(vals)

@@ -12,6 +12,8 @@
 #include <vector>
 
 #include "cpsr_decode.h"
+#include "format_handle.h"
+#include "gpu_format.h"
 #include "spmv_kernels.cuh"
 #include "tile_format.h"
 
@@ -36,10 +38,9 @@ struct DeviceMatrix {
     uint32_t *vals = nullptr;
     uint16_t *cols = nullptr;
         uint32_t *slice_rows = nullptr;
-    hsb::TileDesc *tiles = nullptr;
     void release() {
-        cudaFree(vals); cudaFree(cols); cudaFree(slice_rows); cudaFree(tiles);
-        vals = nullptr; cols = nullptr; slice_rows = nullptr; tiles = nullptr;
+        cudaFree(vals); cudaFree(cols); cudaFree(slice_rows);
+        vals = nullptr; cols = nullptr; slice_rows = nullptr;
     }
 };
 
@@ -57,8 +58,9 @@ struct hsb_ctx {
     uint32_t rows_per_part = 0, n_row_parts = 0, n_col_tiles = 0, tile_cols = 0;
     uint64_t n_slices = 0, n_streams = 0, n_elems = 0, format_bytes = 0;
     std::vector<uint32_t> part_slice_begin;
+    hsb::TiledMatrix meta;                // geometry of the resident matrix (tiles, slice list; no payload)
     std::vector<DeviceMatrix> mats;       // [0] + replicas
-    size_t sz_vals = 0, sz_cols = 0, sz_rows = 0, sz_tiles = 0;
+    size_t sz_vals = 0, sz_cols = 0, sz_rows = 0;
     unsigned next_replica = 0;
     // launch plans: slot 0 = whole matrix, slot 1 + j = row partition j
     uint32_t *d_cta_seg = nullptr;        // [slots][sm_count + 1]
@@ -98,28 +100,37 @@ void free_matrix(hsb_ctx *c) {
     c->have_matrix = false;
 }
 
+int install_matrix(hsb_ctx *c, const hsb::TiledMatrix &M, const DeviceMatrix &d, size_t n_elems, size_t n_slices);
+
 int upload_tiled(hsb_ctx *c, const hsb::TiledMatrix &M) {
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     free_matrix(c);
+    DeviceMatrix d;
+    CUDA_TRY(cudaMalloc(&d.vals, M.vals.size() * 4 + 16));
+    CUDA_TRY(cudaMalloc(&d.cols, M.cols16.size() * 2 + 16));
+    CUDA_TRY(cudaMalloc(&d.slice_rows, M.slice_rows.size() * 4 + 16));
+    CUDA_TRY(cudaMemcpyAsync(d.vals, M.vals.data(), M.vals.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.cols, M.cols16.data(), M.cols16.size() * 2, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.slice_rows, M.slice_rows.data(), M.slice_rows.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    return install_matrix(c, M, d, M.n_elems(), M.n_slices());
+}
+
+// take ownership of a device-resident tile-stream matrix; M supplies the geometry for the planner
+int install_matrix(hsb_ctx *c, const hsb::TiledMatrix &M, const DeviceMatrix &d, size_t n_elems, size_t n_slices) {
     c->rows = M.rows; c->cols = M.cols; c->nnz = M.nnz;
     c->rows_per_part = M.rows_per_part; c->n_row_parts = M.n_row_parts;
     c->n_col_tiles = M.n_col_tiles; c->tile_cols = M.tile_cols;
-    c->n_slices = M.n_slices(); c->n_streams = M.n_streams; c->n_elems = M.n_elems();
-    c->format_bytes = M.format_bytes();
+    c->n_slices = n_slices; c->n_streams = M.n_streams; c->n_elems = n_elems;
+    c->sz_vals = n_elems * 4; c->sz_cols = n_elems * 2;
+    c->sz_rows = n_slices * hsb::kLanes * 4;
+    c->format_bytes = c->sz_vals + c->sz_cols + c->sz_rows;
     c->part_slice_begin = M.part_slice_begin;
-    c->sz_vals = M.vals.size() * 4; c->sz_cols = M.cols16.size() * 2;
-    c->sz_rows = M.slice_rows.size() * 4;
-    c->sz_tiles = M.tiles.size() * sizeof(hsb::TileDesc);
-    DeviceMatrix d;
-    CUDA_TRY(cudaMalloc(&d.vals, c->sz_vals + 16));
-    CUDA_TRY(cudaMalloc(&d.cols, c->sz_cols + 16));
-    CUDA_TRY(cudaMalloc(&d.slice_rows, c->sz_rows + 16));
-    CUDA_TRY(cudaMalloc(&d.tiles, c->sz_tiles + 16));
-    CUDA_TRY(cudaMemcpyAsync(d.vals, M.vals.data(), c->sz_vals, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(d.cols, M.cols16.data(), c->sz_cols, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(d.slice_rows, M.slice_rows.data(), c->sz_rows, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(d.tiles, M.tiles.data(), c->sz_tiles, cudaMemcpyHostToDevice, c->stream));
+    c->meta = hsb::TiledMatrix();
+    c->meta.rows = M.rows; c->meta.cols = M.cols; c->meta.nnz = M.nnz; c->meta.rows_per_part = M.rows_per_part;
+    c->meta.n_row_parts = M.n_row_parts; c->meta.n_col_tiles = M.n_col_tiles; c->meta.tile_cols = M.tile_cols;
+    c->meta.n_streams = M.n_streams; c->meta.slices = M.slices; c->meta.tiles = M.tiles;
+    c->meta.part_slice_begin = M.part_slice_begin;
     c->mats.push_back(d);
     // cost-balanced work plans for the whole-matrix launch and for each row partition
     const uint32_t G = (uint32_t)c->sm_count, T = M.n_col_tiles;
@@ -325,6 +336,55 @@ int hsb_upload_matrix_csr(hsb_ctx *c, uint32_t rows, uint32_t cols, const uint32
     return upload_tiled(c, M);
 }
 
+int hsb_upload_matrix_csr_device(hsb_ctx *c, uint32_t rows, uint32_t cols, uint64_t nnz, const uint32_t *d_indptr,
+                                 const uint32_t *d_indices, const void *d_vals, uint32_t rows_per_partition) {
+    if (!c || !d_indptr || (nnz && (!d_indices || !d_vals))) return set_err(HSB_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    auto t0 = std::chrono::steady_clock::now();
+    free_matrix(c);
+    hsb::TiledMatrix M;
+    hsb::DeviceFormat f;
+    std::string err;
+    cudaError_t e = hsb::build_tiled_gpu(rows, cols, nnz, d_indptr, d_indices, (const uint32_t *)d_vals,
+                                         rows_per_partition, hsb::choose_tile_cols(cols), c->stream, &M, &f, &err);
+    if (e != cudaSuccess) {
+        cudaFree(f.vals); cudaFree(f.cols); cudaFree(f.slice_rows);
+        cudaGetLastError();
+        if (!err.empty()) return set_err(HSB_EINVAL, "malformed CSR: " + err);
+        return set_err(HSB_ECUDA, std::string("GPU formatting failed: ") + cudaGetErrorString(e));
+    }
+    c->preprocess_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    DeviceMatrix d;
+    d.vals = f.vals; d.cols = f.cols; d.slice_rows = f.slice_rows;
+    if (!d.vals) {                                       // empty matrix: the kernel still wants valid pointers
+        CUDA_TRY(cudaMalloc(&d.vals, 16)); CUDA_TRY(cudaMalloc(&d.cols, 16)); CUDA_TRY(cudaMalloc(&d.slice_rows, 16));
+    }
+    return install_matrix(c, M, d, f.n_elems, f.n_slices);
+}
+
+int hsb_upload_matrix_csr_gpu(hsb_ctx *c, uint32_t rows, uint32_t cols, const uint32_t *indptr,
+                              const uint32_t *indices, const void *vals, uint32_t rows_per_partition) {
+    if (!c || !indptr || (rows && indptr[rows] && (!indices || !vals))) return set_err(HSB_EINVAL, "null argument");
+    for (uint32_t r = 0; r < rows; r++)
+        if (indptr[r + 1] < indptr[r]) return set_err(HSB_EINVAL, "malformed CSR: indptr is not monotone");
+    if (rows && indptr[0] != 0) return set_err(HSB_EINVAL, "malformed CSR: indptr[0] must be 0");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const uint64_t nnz = rows ? indptr[rows] : 0;
+    uint32_t *d_ip = nullptr, *d_ix = nullptr, *d_v = nullptr;
+    CUDA_TRY(cudaMalloc(&d_ip, ((size_t)rows + 1) * 4));
+    CUDA_TRY(cudaMalloc(&d_ix, std::max<uint64_t>(nnz, 1) * 4));
+    CUDA_TRY(cudaMalloc(&d_v, std::max<uint64_t>(nnz, 1) * 4));
+    CUDA_TRY(cudaMemcpyAsync(d_ip, indptr, ((size_t)rows + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    if (nnz) {
+        CUDA_TRY(cudaMemcpyAsync(d_ix, indices, nnz * 4, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_v, vals, nnz * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc = hsb_upload_matrix_csr_device(c, rows, cols, nnz, d_ip, d_ix, d_v, rows_per_partition);
+    cudaFree(d_ip); cudaFree(d_ix); cudaFree(d_v);
+    return rc;
+}
+
 int hsb_upload_matrix_cpsr(hsb_ctx *c, const void *const ch[HSB_NUM_HBM_CHANNELS],
                            const size_t ch_packets[HSB_NUM_HBM_CHANNELS], unsigned num_row_partitions,
                            unsigned num_col_partitions, unsigned num_rows, unsigned num_cols) {
@@ -482,11 +542,9 @@ int hsb_set_replicas(hsb_ctx *c, int n) {
         CUDA_TRY(cudaMalloc(&d.vals, c->sz_vals + 16));
         CUDA_TRY(cudaMalloc(&d.cols, c->sz_cols + 16));
             CUDA_TRY(cudaMalloc(&d.slice_rows, c->sz_rows + 16));
-        CUDA_TRY(cudaMalloc(&d.tiles, c->sz_tiles + 16));
         CUDA_TRY(cudaMemcpyAsync(d.vals, s.vals, c->sz_vals, cudaMemcpyDeviceToDevice, c->stream));
         CUDA_TRY(cudaMemcpyAsync(d.cols, s.cols, c->sz_cols, cudaMemcpyDeviceToDevice, c->stream));
         CUDA_TRY(cudaMemcpyAsync(d.slice_rows, s.slice_rows, c->sz_rows, cudaMemcpyDeviceToDevice, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(d.tiles, s.tiles, c->sz_tiles, cudaMemcpyDeviceToDevice, c->stream));
         c->mats.push_back(d);
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -545,6 +603,22 @@ int hsb_debug_trace(hsb_ctx *c, unsigned long long *out, size_t capacity) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaMemcpy(out, c->d_trace, n * 8, cudaMemcpyDeviceToHost));
     return (int)n;
+}
+
+hsb_format *hsb_format_from_context(hsb_ctx *c) {
+    if (!c || !c->have_matrix) { set_err(HSB_ESTATE, "no resident matrix"); return nullptr; }
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) return nullptr;
+    hsb_format *f = new hsb_format;
+    f->M = c->meta;
+    f->M.vals.resize(c->n_elems);
+    f->M.cols16.resize(c->n_elems);
+    f->M.slice_rows.resize(c->n_slices * hsb::kLanes);
+    const DeviceMatrix &d = c->mats[0];
+    bool ok = cudaMemcpy(f->M.vals.data(), d.vals, c->n_elems * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+              cudaMemcpy(f->M.cols16.data(), d.cols, c->n_elems * 2, cudaMemcpyDeviceToHost) == cudaSuccess &&
+              cudaMemcpy(f->M.slice_rows.data(), d.slice_rows, c->n_slices * hsb::kLanes * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (!ok) { delete f; set_err(HSB_ECUDA, "download of the device format failed"); return nullptr; }
+    return f;
 }
 
 int hsb_debug_plan(hsb_ctx *c, uint32_t *steps, uint32_t *slices, size_t capacity) {

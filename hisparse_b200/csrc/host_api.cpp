@@ -7,11 +7,8 @@
 #include <vector>
 
 #include "cpsr_decode.h"
+#include "format_handle.h"
 #include "tile_format.h"
-
-struct hsb_format {
-    hsb::TiledMatrix M;
-};
 
 extern "C" {
 

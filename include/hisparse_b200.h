@@ -96,6 +96,15 @@ int hsb_upload_matrix_cpsr(hsb_ctx *ctx, const void *const ch[HSB_NUM_HBM_CHANNE
 int hsb_upload_matrix_csr(hsb_ctx *ctx, uint32_t rows, uint32_t cols, const uint32_t *indptr,
                           const uint32_t *indices, const void *vals, uint32_t rows_per_partition);
 
+/* The same with the formatting done ON THE GPU (device-wide sorts and scans instead of host threads):
+ * from a host CSR, or from a CSR that already lives in device memory (32-bit device pointers to
+ * indptr[rows+1], indices[nnz], vals[nnz]); the device CSR is not modified and may be freed afterwards. */
+int hsb_upload_matrix_csr_gpu(hsb_ctx *ctx, uint32_t rows, uint32_t cols, const uint32_t *indptr,
+                              const uint32_t *indices, const void *vals, uint32_t rows_per_partition);
+int hsb_upload_matrix_csr_device(hsb_ctx *ctx, uint32_t rows, uint32_t cols, uint64_t nnz,
+                                 const uint32_t *d_indptr, const uint32_t *d_indices, const void *d_vals,
+                                 uint32_t rows_per_partition);
+
 /* == vector_buf on HBM[20] + migrate (sw/host.cpp:282-298). x_packed: num_cols 32-bit words.
  * Asynchronous on a copy stream; the next hsb_spmv* waits for it. */
 int hsb_upload_vector(hsb_ctx *ctx, const void *x_packed, unsigned num_cols);
@@ -155,6 +164,8 @@ typedef struct hsb_format hsb_format;
  * tile_cols == 0 picks the width automatically. NULL on malformed input. */
 hsb_format *hsb_format_build(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uint32_t *indices,
                              const void *vals, uint32_t rows_per_partition, uint32_t tile_cols);
+/* Copy of the matrix resident on the device (whichever way it was built) for inspection. */
+hsb_format *hsb_format_from_context(hsb_ctx *ctx);
 int hsb_format_stats(const hsb_format *f, hsb_stats *out);
 /* Walk the chunk stream the way the kernel addresses it (value slots, end-of-segment flags,
  * seg_row, chunk descriptors) and rebuild the CSR. indices/vals hold nnz words each. Returns

@@ -284,3 +284,50 @@ def test_cpp_host_driver(gpu, impl):
     r = subprocess.run([os.path.join(host, "bin", "host_" + impl)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "===== All Test Passed! =====" in r.stdout
+
+
+# ------------------------------------------------------------------------------------------
+# GPU-side preprocessing (hsb_upload_matrix_csr_gpu): same results, structurally valid format
+# ------------------------------------------------------------------------------------------
+GPU_FORMAT_CASES = [
+    ("empty", lambda: (128, 64, np.zeros(129, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.float32)), 0),
+    ("dense128", lambda: matgen.dense_csr(128, 128), 0),
+    ("uniform_unsorted_cols", lambda: matgen.uniform_sparse_csr(1000, 1024, 10), 0),
+    ("multi_tile_70000", lambda: matgen.random_csr(900, 70000, 0.003, 7), 0),
+    ("rmat_row_partitions", lambda: matgen.rmat_csr(20000, 300000, 9), 4096),
+    ("rmat_60000", lambda: matgen.rmat_csr(60000, 2500000, 12), 0),
+    ("one_long_row", lambda: (4, 70000, np.array([0, 0, 70000, 70000, 70001], np.uint32),
+                              np.concatenate([np.arange(70000), [3]]).astype(np.uint32),
+                              np.full(70001, 0.001, np.float32)), 0),
+]
+
+
+@pytest.mark.parametrize("name,make,rpp", GPU_FORMAT_CASES, ids=[c[0] for c in GPU_FORMAT_CASES])
+def test_gpu_built_format(gpu, port, name, make, rpp):
+    rows, cols, indptr, indices, data = make()
+    words = port.quantize(data)
+    xw = port.quantize(np.random.default_rng(1).random(cols, dtype=np.float32))
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    ctx.upload_matrix_csr(rows, cols, indptr, indices, words, rpp, on_gpu=True)
+    # 1. the device-built format decodes back to the CSR it came from
+    f = capi.Format.from_context(ctx)
+    ip, ix, vv = f.expand()
+    assert np.array_equal(ip, indptr)
+    r = np.repeat(np.arange(rows, dtype=np.int64), np.diff(indptr.astype(np.int64)))
+    a = np.lexsort((words, indices, r))
+    b = np.lexsort((vv, ix, r))
+    assert np.array_equal(indices[a], ix[b]) and np.array_equal(words[a], vv[b])
+    # 2. and the SpMV over it is bit-exact
+    ctx.upload_vector(xw)
+    if rpp:
+        nparts = (rows + rpp - 1) // rpp
+        for j in range(nparts):
+            ctx.spmv()          # whole-matrix launches and ...
+        ctx.spmv()
+    ctx.spmv()
+    assert np.array_equal(ctx.download_result(), port.spmv_q824(indptr, indices, words, xw))
+    # 3. same geometry as the host builder (streams, slices, padded slots)
+    sg, sh = ctx.stats(), capi.Format(rows, cols, indptr, indices, words, rpp).stats()
+    for k in ("n_streams", "n_slices", "n_elems", "n_col_tiles", "tile_cols", "n_row_parts"):
+        assert sg[k] == sh[k], k
+    ctx.close()

@@ -109,3 +109,10 @@ def test_cpsr_decode_rejects_truncated_image(port):
     images[3] = images[3][:-1]
     with pytest.raises(capi.HsbError):
         capi.cpsr_to_csr(0, images, 1, 1, rows, cols)
+
+
+def test_quantize_helper_matches_oracle(port):
+    rng = np.random.default_rng(0)
+    v = np.concatenate([rng.random(50000, dtype=np.float32) * 300 - 10,
+                        np.array([0, 1, 255.99999, 256, 1e9, -1, 2 ** -25, 3 * 2 ** -25, np.nan, np.inf], np.float32)])
+    assert np.array_equal(matgen.quantize_q824(v), port.quantize(v))

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--replicas", type=int, default=0)
+    ap.add_argument("--gpu-format", action="store_true")
     a = ap.parse_args()
     rows, cols, indptr, indices, data = make(a.config)
     r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
@@ -36,7 +37,10 @@ def main():
     if a.impl == "fixed":
         data, x = matgen.quantize_q824(data * np.float32(0.05)), matgen.quantize_q824(x)
     ctx = capi.Context(0, a.impl)
-    ctx.upload_matrix_csr(r2, c2, ip2, indices, data)
+    import time as _t
+    t0 = _t.perf_counter()
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, data, on_gpu=a.gpu_format)
+    t_up = _t.perf_counter() - t0
     st = ctx.stats()
     ctx.set_replicas(a.replicas or max(2, int(np.ceil(2.5 * 126 * 2 ** 20 / max(st["format_bytes"], 1)))))
     ctx.upload_vector(x)
@@ -45,6 +49,7 @@ def main():
         print("config %s impl %s nnz %d: %.2f us/spmv, kernel %.2f us, %.0f GOPS, alg %.0f GB/s, fmt %.0f GB/s" % (
             a.config, a.impl, st["nnz"], step * 1e3, kern * 1e3, 2 * st["nnz"] / step / 1e6,
             st["algorithmic_bytes"] / kern / 1e6, st["format_bytes"] / kern / 1e6))
+        print("upload+format wall %.3f s, preprocess %.4f s (%s)" % (t_up, st["preprocess_seconds"], "GPU" if a.gpu_format else "host"))
         print(st)
     else:
         for _ in range(a.spmv):
