@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -326,6 +327,9 @@ void hsb_host_free(void *p) { if (p) cudaFreeHost(p); }
 int hsb_upload_matrix_csr(hsb_ctx *c, uint32_t rows, uint32_t cols, const uint32_t *indptr,
                           const uint32_t *indices, const void *vals, uint32_t rows_per_partition) {
     if (!c || !indptr || (rows && indptr[rows] && (!indices || !vals))) return set_err(HSB_EINVAL, "null argument");
+    // formatting runs on the device by default (gpu_format.cu); HSB_HOST_FORMAT=1 selects the host builder
+    static const bool host_format = std::getenv("HSB_HOST_FORMAT") != nullptr;
+    if (!host_format) return hsb_upload_matrix_csr_gpu(c, rows, cols, indptr, indices, vals, rows_per_partition);
     auto t0 = std::chrono::steady_clock::now();
     hsb::TiledMatrix M;
     std::string err;
@@ -404,12 +408,10 @@ int hsb_upload_matrix_cpsr(hsb_ctx *c, const void *const ch[HSB_NUM_HBM_CHANNELS
     if (!hsb::cpsr_decode(c->cfg, imgs, ch_packets, num_row_partitions, num_col_partitions, 0, num_row_partitions,
                           rows_in.data(), num_cols, &csr, &err))
         return set_err(HSB_EINVAL, "malformed CPSR image: " + err);
-    hsb::TiledMatrix M;
-    if (!hsb::build_tiled(csr.rows, csr.cols, csr.indptr.data(), csr.indices.data(), csr.vals.data(),
-                          c->cfg.ob_size, hsb::choose_tile_cols(csr.cols), 0, &M, &err))
-        return set_err(HSB_EINVAL, "malformed CPSR image: " + err);
+    int rc = hsb_upload_matrix_csr(c, csr.rows, csr.cols, csr.indptr.data(), csr.indices.data(), csr.vals.data(),
+                                   c->cfg.ob_size);
     c->preprocess_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    return upload_tiled(c, M);
+    return rc;
 }
 
 int hsb_upload_vector(hsb_ctx *c, const void *x_packed, unsigned num_cols) {
