@@ -400,6 +400,25 @@ int hsb_upload_matrix_cpsr(hsb_ctx *c, const void *const ch[HSB_NUM_HBM_CHANNELS
     auto t0 = std::chrono::steady_clock::now();
     const uint32_t *imgs[16];
     for (int i = 0; i < 16; i++) imgs[i] = (const uint32_t *)ch[i];
+    static const bool host_format = std::getenv("HSB_HOST_FORMAT") != nullptr;
+    if (!host_format) {
+        // the channel images go to HBM as they are; decoding and re-formatting run on the device
+        CUDA_TRY(cudaSetDevice(c->device));
+        uint32_t *d_ip = nullptr, *d_ix = nullptr, *d_v = nullptr;
+        uint64_t nnz = 0;
+        std::string derr;
+        cudaError_t e = hsb::cpsr_decode_gpu(c->cfg, imgs, ch_packets, num_row_partitions, num_col_partitions, num_rows,
+                                             num_cols, c->stream, &d_ip, &d_ix, &d_v, &nnz, &derr);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            if (!derr.empty()) return set_err(HSB_EINVAL, "malformed CPSR image: " + derr);
+            return set_err(HSB_ECUDA, std::string("GPU decoding failed: ") + cudaGetErrorString(e));
+        }
+        int rc = hsb_upload_matrix_csr_device(c, num_rows, num_cols, nnz, d_ip, d_ix, d_v, c->cfg.ob_size);
+        cudaFree(d_ip); cudaFree(d_ix); cudaFree(d_v);
+        c->preprocess_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return rc;
+    }
     std::vector<uint32_t> rows_in(num_row_partitions);
     for (unsigned j = 0; j < num_row_partitions; j++)
         rows_in[j] = std::min<uint64_t>(c->cfg.ob_size, (uint64_t)num_rows - (uint64_t)j * c->cfg.ob_size);

@@ -331,3 +331,35 @@ def test_gpu_built_format(gpu, port, name, make, rpp):
     for k in ("n_streams", "n_slices", "n_elems", "n_col_tiles", "tile_cols", "n_row_parts"):
         assert sg[k] == sh[k], k
     ctx.close()
+
+
+def test_cpsr_upload_rejects_truncated_image(gpu, port):
+    cfg = capi.get_config(0)
+    rows, cols, indptr, indices, data = matgen.random_csr(256, 512, 0.05, 9)
+    m = port.csr2cpsr(rows, cols, indptr, indices, port.quantize(data), 8, cfg.logical_ob_size,
+                      cfg.logical_vb_size, 16, False, hsoracle.VAL_Q824)
+    images = m.channel_images(1)
+    images[3] = images[3][:-1]
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    with pytest.raises(capi.HsbError):
+        ctx.upload_matrix_cpsr(images, 1, 1, rows, cols)
+    ctx.close()
+
+
+def test_cpsr_images_large_float_stall(gpu, port):
+    """float_stall: 8-way interleaved virtual channels, rows rounded to 1024, skip-empty-rows markers,
+    three column partitions -- through the on-device CPSR decoder."""
+    cfg = capi.get_config(capi.IMPL_FLOAT_STALL)
+    IF = cfg.interleave_factor
+    rows, cols, indptr, indices, data = matgen.rmat_csr(70000, 1500000, 41, values="normal")
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128 * IF, 8)
+    x = np.zeros(c2, np.float32)
+    x[:cols] = np.random.default_rng(2).random(cols, dtype=np.float32) * 2 - 1
+    m = port.csr2cpsr(r2, c2, ip2, indices, data.view(np.uint32), 8, cfg.logical_ob_size, cfg.logical_vb_size,
+                      16 * IF, True, hsoracle.VAL_FLOAT_BITS)
+    ctx = capi.Context(0, capi.IMPL_FLOAT_STALL)
+    ctx.upload_matrix_cpsr(m.channel_images(IF), m.n_row_parts, m.n_col_parts, r2, c2)
+    ctx.upload_vector(x)
+    ctx.spmv_row_partition(0, r2 // 16, m.n_col_parts, m.n_col_parts * m.n_row_parts, c2)
+    check_float(ctx.download_result(), port, ip2, indices, data, x)
+    ctx.close()
