@@ -211,6 +211,8 @@ class Ref:
         L.ref_compute_ref.argtypes = [C.c_uint32, C.c_uint32, u32p, u32p, f32p, f32p, f32p]
         L.ref_time_compute_ref.argtypes = [C.c_uint32, C.c_uint32, u32p, u32p, f32p, f32p, f32p, C.c_int]
         L.ref_time_compute_ref.restype = C.c_double
+        L.ref_time_compute_ref_mt.argtypes = [C.c_uint32, C.c_uint32, u32p, u32p, f32p, f32p, f32p, C.c_int, C.c_int]
+        L.ref_time_compute_ref_mt.restype = C.c_double
         L.ref_test_harness.argtypes = [C.c_uint32, C.c_uint32, u32p, u32p, f32p, C.c_int, C.c_uint]
         L.ref_selftest.restype = C.c_int
 
@@ -248,6 +250,13 @@ class Ref:
         y = np.empty(rows, np.float32)
         return float(self.L.ref_time_compute_ref(rows, cols, _u32(indptr), _u32(indices), _f32(data),
                                                  _f32(x), y, runs))
+
+    def time_compute_ref_mt(self, rows, cols, indptr, indices, data, x, runs, threads, y=None):
+        """compute_ref on `threads` nnz-balanced row blocks at once (every host core): seconds per SpMV"""
+        if y is None:
+            y = np.empty(rows, np.float32)
+        return float(self.L.ref_time_compute_ref_mt(rows, cols, _u32(indptr), _u32(indices), _f32(data),
+                                                    _f32(x), y, runs, threads))
 
     def test_harness(self, rows, cols, indptr, indices, data, skip, seed=1):
         return bool(self.L.ref_test_harness(rows, cols, _u32(indptr), _u32(indices), _f32(data),

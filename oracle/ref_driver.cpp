@@ -12,9 +12,11 @@
 #include "csim.cpp"   // resolved with -I/root/reference/spmv_csim
 #undef main
 
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <sstream>
+#include <thread>
 
 namespace {
 
@@ -165,6 +167,49 @@ double ref_time_compute_ref(uint32_t rows, uint32_t cols, const uint32_t *indptr
     for (int r = 0; r < runs; r++) compute_ref(m, xv, yv);
     clock_gettime(CLOCK_MONOTONIC, &t1);
     std::memcpy(y, yv.data(), sizeof(float) * rows);
+    return ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec)) / runs;
+}
+
+// The same reference loop on all host threads: the rows are cut into `threads` contiguous blocks of
+// about equal non-zeros and every thread runs the UNMODIFIED compute_ref on its block's CSR (x shared
+// by value per thread, as compute_ref takes it). Wall time from a common start to the last finisher.
+double ref_time_compute_ref_mt(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uint32_t *indices,
+                               const float *data, const float *x, float *y, int runs, int threads) {
+    if (threads < 1) threads = 1;
+    std::vector<uint32_t> cut(threads + 1, rows);
+    cut[0] = 0;
+    for (int t = 1; t < threads; t++) {
+        const uint64_t target = (uint64_t)indptr[rows] * t / threads;
+        uint32_t lo = cut[t - 1], hi = rows;
+        while (lo < hi) { uint32_t mid = lo + (hi - lo) / 2; if (indptr[mid] < target) lo = mid + 1; else hi = mid; }
+        cut[t] = lo;
+    }
+    std::vector<spmv::io::CSRMatrix<float>> blocks(threads);
+    std::vector<std::vector<float>> xs(threads, std::vector<float>(x, x + cols)), ys(threads);
+    for (int t = 0; t < threads; t++) {
+        const uint32_t r0 = cut[t], r1 = cut[t + 1], e0 = indptr[r0];
+        std::vector<uint32_t> ip(r1 - r0 + 1);
+        for (uint32_t r = r0; r <= r1; r++) ip[r - r0] = indptr[r] - e0;
+        blocks[t] = make_csr(r1 - r0, cols, ip.data(), indices + e0, data + e0);
+        compute_ref(blocks[t], xs[t], ys[t]);                       // warm
+    }
+    std::atomic<int> ready(0);
+    std::atomic<bool> go(false);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&, t] {
+            ready++;
+            while (!go.load(std::memory_order_acquire)) {}
+            for (int r = 0; r < runs; r++) compute_ref(blocks[t], xs[t], ys[t]);
+        });
+    while (ready.load() < threads) {}
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    go.store(true, std::memory_order_release);
+    for (auto &th : pool) th.join();
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    for (int t = 0; t < threads; t++)
+        if (cut[t + 1] > cut[t]) std::memcpy(y + cut[t], ys[t].data(), sizeof(float) * (cut[t + 1] - cut[t]));
     return ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec)) / runs;
 }
 
