@@ -302,40 +302,54 @@ def main():
     # upload -> spmv -> download+finish (sw/host.cpp:293-371); (b) the same three calls with the
     # asynchronous download, so that upload(k+1), SpMV(k) and download(k-1) overlap on the library's
     # copy streams (two host buffers in rotation) -- the way a throughput-oriented caller uses it.
-    def same(got):
+    # Two different vectors alternate, so that a stale x or y anywhere in the pipeline shows up in the result.
+    xw2 = np.ascontiguousarray(xw[::-1])
+    ctx.upload_vector(xw2)
+    ctx.spmv()
+    y2 = ctx.download_result()
+    want = (y, y2)
+
+    def same(got, k):
         # fixed point: sums of non-negative integers are order independent -> identical words; float: the
         # row updates are fp32 atomics whose order varies from launch to launch -> tolerance only
         if impl == "fixed":
-            ok = np.array_equal(got, y)
+            ok = np.array_equal(got, want[k])
         else:
-            a, b = got.view(np.float32).astype(np.float64), y.view(np.float32).astype(np.float64)
+            a, b = got.view(np.float32).astype(np.float64), want[k].view(np.float32).astype(np.float64)
             ok = bool(np.all(np.abs(a - b) <= 1e-4 * np.maximum(np.abs(b), 1e-3)))
         if not ok:
             ctx.close()
-            raise SystemExit("bench: end-to-end result differs from the device-resident run")
+            raise SystemExit("bench: end-to-end result %d differs from the device-resident run" % k)
 
     px = [capi.PinnedArray(c2) for _ in range(2)]
     py = [capi.PinnedArray(r2) for _ in range(2)]
-    for b_ in px:
-        b_.array[:] = xw
-    n_e2e = max(64, min(args.steps * B, 1024))
-    for _ in range(16):
-        ctx.upload_vector(px[0].array); ctx.spmv(); ctx.download_result(py[0].array)
+    px[0].array[:] = xw
+    px[1].array[:] = xw2
+    xh, yh = [b_.array for b_ in px], [b_.array for b_ in py]
+    n_e2e = max(64, min(args.steps * B, 4096))
+    n_e2e += n_e2e & 1
+    ctx.time_e2e(xh, yh, 16, async_download=False)
+    barrier()
+    # (a) strictly synchronous, (b) pipelined; both issued from C by hsb_time_e2e through the public entry points
+    n_sync = max(64, n_e2e // 4)
+    e2e_sync_s = ctx.time_e2e(xh, yh, n_sync + (n_sync & 1), async_download=False)
+    same(yh[0], 0)
+    same(yh[1], 1)
+    for b_ in yh:
+        b_[:] = 0
+    barrier()
+    e2e_s = ctx.time_e2e(xh, yh, n_e2e, async_download=True)
+    same(yh[0], 0)
+    same(yh[1], 1)
+    # the same pipelined sequence issued call by call from Python (ctypes): what the pytest glue sees
     barrier()
     t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        ctx.upload_vector(px[0].array); ctx.spmv(); ctx.download_result(py[0].array)
+    for k in range(256):
+        ctx.upload_vector(xh[k & 1]); ctx.spmv(); ctx.download_result_async(yh[k & 1])
     ctx.sync()
-    e2e_sync_s = (time.perf_counter() - t0) / n_e2e
-    same(py[0].array)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(n_e2e):
-        ctx.upload_vector(px[k & 1].array); ctx.spmv(); ctx.download_result_async(py[k & 1].array)
-    ctx.sync()
-    e2e_s = (time.perf_counter() - t0) / n_e2e
-    same(py[0].array)
-    same(py[1].array)
+    e2e_py_s = (time.perf_counter() - t0) / 256
+    same(yh[0], 0)
+    same(yh[1], 1)
     if dist is not None:
         import torch
         t = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device="cuda:%d" % local)
@@ -378,9 +392,13 @@ def main():
             "e2e": {"value": 2.0 * nnz_all / e2e_s / 1e9, "unit": "GOPS", "h2d_bytes_per_step": B * c2 * 4,
                     "d2h_bytes_per_step": B * r2 * 4, "ms_per_spmv": 1e3 * e2e_s,
                     "synchronous_value": 2.0 * nnz_all / e2e_sync_s / 1e9, "synchronous_ms_per_spmv": 1e3 * e2e_sync_s,
-                    "what": "per SpMV: hsb_upload_vector(pinned x) + hsb_spmv + hsb_download_result_async(pinned y), "
-                            "copies and kernels overlapping across consecutive SpMVs; synchronous_* = the same with "
-                            "the blocking hsb_download_result after every SpMV; matrix resident as in sw/benchmark.cpp"},
+                    "python_glue_ms_per_spmv": 1e3 * e2e_py_s,
+                    "what": "per SpMV: hsb_upload_vector(pinned x) + hsb_spmv + hsb_download_result_async(pinned y) "
+                            "issued from C (hsb_time_e2e), two x / y host buffers alternating, copies and kernels "
+                            "overlapping across consecutive SpMVs, wall clock incl. the final hsb_sync; synchronous_* = "
+                            "the same with the blocking hsb_download_result after every SpMV; python_glue_* = the "
+                            "pipelined sequence issued call by call through ctypes; matrix resident as in "
+                            "sw/benchmark.cpp"},
             "gpu_launches": int(launches2 - launches1),
             "gpu_launches_per_spmv": (launches2 - launches1) / float(args.steps * B),
             "clocks": sampler.summary(),

@@ -41,6 +41,11 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class DeviceCsrStruct(C.Structure):
+    _fields_ = [("rows", C.c_uint32), ("cols", C.c_uint32), ("nnz", C.c_uint64), ("d_indptr", C.c_void_p),
+                ("d_indices", C.c_void_p), ("d_vals", C.c_void_p), ("device", C.c_int)]
+
+
 def build(force=False):
     """Compile hisparse_b200/libhisparse_b200.so for sm_100a with nvcc (in-tree)."""
     args = ["make", "-s", "-C", os.path.join(HERE, "csrc")]
@@ -94,10 +99,14 @@ def lib():
     L.hsb_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.hsb_set_replicas.argtypes = [vp, C.c_int]
     L.hsb_time_spmv.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.hsb_time_e2e.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.c_uint, C.c_uint, C.c_int, C.c_int,
+                               C.POINTER(C.c_double)]
     for n in ("hsb_device_x", "hsb_device_y", "hsb_stream"):
         getattr(L, n).argtypes = [vp]
         getattr(L, n).restype = vp
+    L.hsb_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     L.hsb_debug_trace.argtypes = [vp, vp, sz]
+    L.hsb_debug_timeline.argtypes = [vp, vp, sz]
     L.hsb_debug_plan.argtypes = [vp, vp, vp, sz]
     L.hsb_format_build.argtypes = [u32, u32, vp, vp, vp, u32, u32]
     L.hsb_format_build.restype = vp
@@ -109,6 +118,12 @@ def lib():
     L.hsb_format_free.restype = None
     L.hsb_cpsr_to_csr.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(sz), C.c_uint, C.c_uint, C.c_uint, C.c_uint,
                                   vp, vp, vp, sz, C.POINTER(sz)]
+    L.hsb_synth_powerlaw_csr_device.argtypes = [C.c_int, u32, u32, C.c_uint64, C.c_double, C.c_double, u32, u32,
+                                                C.c_double, C.c_uint64, C.c_int, C.c_float, C.POINTER(DeviceCsrStruct)]
+    L.hsb_device_csr_download.argtypes = [C.POINTER(DeviceCsrStruct), vp, vp, vp]
+    L.hsb_device_csr_free.argtypes = [C.POINTER(DeviceCsrStruct)]
+    L.hsb_device_csr_free.restype = None
+    L.hsb_synth_last_error.restype = C.c_char_p
     _lib = L
     return L
 
@@ -167,6 +182,44 @@ class PinnedArray:
             pass
 
 
+class DeviceCsr:
+    """A CSR that lives in device memory (hsb_device_csr): here always a synthetic power-law shard
+    generated on the GPU (BASELINE config C5)."""
+
+    def __init__(self, st):
+        self.st = st
+
+    @classmethod
+    def powerlaw(cls, device, rows, cols, first_global_row=0, mean_degree=20.0, alpha=2.1, max_degree=10 ** 6,
+                 band_half_width=1 << 20, band_fraction=0.8, seed=0xC0FFEE05, q824=False, value_scale=1.0):
+        st = DeviceCsrStruct()
+        rc = lib().hsb_synth_powerlaw_csr_device(device, rows, cols, first_global_row, mean_degree, alpha, max_degree,
+                                                 band_half_width, band_fraction, seed, 1 if q824 else 0, value_scale,
+                                                 C.byref(st))
+        if rc != 0:
+            raise HsbError("hsb_synth_powerlaw_csr_device error %d: %s" % (rc, lib().hsb_synth_last_error().decode()))
+        return cls(st)
+
+    rows = property(lambda self: self.st.rows)
+    cols = property(lambda self: self.st.cols)
+    nnz = property(lambda self: self.st.nnz)
+
+    def download(self):
+        indptr = np.empty(self.rows + 1, np.uint32)
+        indices = np.empty(max(self.nnz, 1), np.uint32)
+        vals = np.empty(max(self.nnz, 1), np.uint32)
+        rc = lib().hsb_device_csr_download(C.byref(self.st), _ptr(indptr), _ptr(indices), _ptr(vals))
+        if rc != 0:
+            raise HsbError("hsb_device_csr_download: " + lib().hsb_synth_last_error().decode())
+        return indptr, indices[:self.nnz], vals[:self.nnz]
+
+    def free(self):
+        if self.st.d_indptr:
+            lib().hsb_device_csr_free(C.byref(self.st))
+
+    __del__ = free
+
+
 class Context:
     """One GPU, one implementation (fixed / float_pob / float_stall): mirrors the reference's
     cl_runtime struct (sw/host.cpp:120-128)."""
@@ -194,6 +247,13 @@ class Context:
         fn = lib().hsb_upload_matrix_csr_gpu if on_gpu else lib().hsb_upload_matrix_csr
         _check(fn(self.h, rows, cols, _ptr(indptr), _ptr(indices), _ptr(vals), rows_per_partition))
         self.rows, self.cols = rows, cols
+
+    def upload_matrix_csr_device(self, dcsr, rows_per_partition=0):
+        """a CSR already in device memory (DeviceCsr): formatted on the GPU, never visits the host"""
+        st = dcsr.st
+        _check(lib().hsb_upload_matrix_csr_device(self.h, st.rows, st.cols, st.nnz, st.d_indptr, st.d_indices,
+                                                  st.d_vals, rows_per_partition))
+        self.rows, self.cols = st.rows, st.cols
 
     def upload_matrix_cpsr(self, images, n_row_parts, n_col_parts, rows, cols):
         imgs, arr, lens = _images_args(images)
@@ -236,6 +296,18 @@ class Context:
         _check(lib().hsb_time_spmv(self.h, warmup, steps, C.byref(a), C.byref(b) if kernel else None))
         return a.value, (b.value if kernel else None)
 
+    def time_e2e(self, x_host, y_host, iters, async_download=True):
+        """hsb_time_e2e: x_host / y_host are two page-locked arrays each (PinnedArray.array); seconds per SpMV"""
+        xs = (C.c_void_p * 2)(*[a.ctypes.data for a in x_host])
+        ys = (C.c_void_p * 2)(*[a.ctypes.data for a in y_host])
+        sec = C.c_double()
+        _check(lib().hsb_time_e2e(self.h, xs, ys, x_host[0].size, y_host[0].size, iters, 1 if async_download else 0,
+                                  C.byref(sec)))
+        return sec.value
+
+    def set_option(self, name, value):
+        _check(lib().hsb_set_option(self.h, name.encode(), int(value)))
+
     def trace(self, arm=None):
         """arm=True/False switches tracing; arm=None returns the [sm_count, 34] stamps of the last launch"""
         if arm is not None:
@@ -246,6 +318,16 @@ class Context:
         if rc < 0:
             _check(rc)
         return out.reshape(self.stats()["sm_count"], -1)
+
+    def timeline(self, arm=None):
+        """arm=True/False switches it; arm=None -> (last launch number, [256, 8] globaltimer stamps in ns)"""
+        if arm is not None:
+            return lib().hsb_debug_timeline(self.h, None, 1 if arm else 0)
+        out = np.zeros(256 * 8, np.uint64)
+        rc = lib().hsb_debug_timeline(self.h, _ptr(out), out.size)
+        if rc < 0:
+            _check(rc)
+        return rc, out.reshape(256, 8)
 
     def plan(self):
         n = self.stats()["sm_count"]

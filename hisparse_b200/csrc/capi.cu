@@ -2,6 +2,7 @@
 // reference's OpenCL host calls (sw/host.cpp:263-371; xrt/includes/xcl2).
 #include "../../include/hisparse_b200.h"
 
+#include <cuda.h>            // types of the stream memory operations only: the entry points are resolved at run time
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -34,6 +35,40 @@ int set_err(int code, const std::string &m) { g_err = m; return code; }
             return set_err(HSB_ECUDA, b__);                                                         \
         }                                                                                           \
     } while (0)
+
+// Stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32) let the copy streams and the
+// SpMV kernels hand buffers to each other through sequence flags in device memory, so that the compute
+// stream carries nothing but kernel launches (an event record or wait between two launches undoes their
+// programmatic-dependent-launch overlap: 16 -> 25 us per SpMV on C2). Resolved through the runtime so
+// that the library has no link-time dependency on libcuda.
+typedef CUresult (*memop32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+memop32_fn g_write32 = nullptr, g_wait32 = nullptr;
+bool load_memops() {
+    static const bool ok = [] {
+        if (std::getenv("HSB_NO_FLAGS")) return false;
+        void *w = nullptr, *q = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &st) != cudaSuccess ||
+            st != cudaDriverEntryPointSuccess || !w) { cudaGetLastError(); return false; }
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &q, cudaEnableDefault, &st) != cudaSuccess ||
+            st != cudaDriverEntryPointSuccess || !q) { cudaGetLastError(); return false; }
+        g_write32 = (memop32_fn)w;
+        g_wait32 = (memop32_fn)q;
+        return true;
+    }();
+    return ok;
+}
+#define MEMOP_TRY(expr)                                                                             \
+    do {                                                                                            \
+        CUresult r__ = (expr);                                                                      \
+        if (r__ != CUDA_SUCCESS) {                                                                  \
+            char b__[256];                                                                          \
+            std::snprintf(b__, sizeof b__, "stream memory operation failed at %s:%d (CUresult %d)", \
+                          __FILE__, __LINE__, (int)r__);                                            \
+            return set_err(HSB_ECUDA, b__);                                                         \
+        }                                                                                           \
+    } while (0)
+enum { kFlagXReady = 0, kFlagYFree = 4, kFlagError = 6, kFlagDoneDev = 7, kNumFlags = 8, kXBuffers = 4, kAccBuffers = 4 };
 
 struct DeviceMatrix {
     uint32_t *vals = nullptr;
@@ -72,20 +107,52 @@ struct hsb_ctx {
     // vectors
     // x is double buffered so that the upload of the next vector (copy stream) overlaps the SpMV that
     // still reads the current one; x_words words each (padded to whole tiles, zero filled)
-    uint32_t *d_x[2] = {nullptr, nullptr};
+    // (three buffers in flag-pipeline mode, so that an upload never has to wait for the launch in flight)
+    uint32_t *d_x[kXBuffers] = {nullptr, nullptr, nullptr, nullptr};
     int x_latest = 0;                     // buffer the next launch reads
     bool x_dirty = false;                 // uploaded since the last launch: the launch must wait for the copy
-    uint32_t *d_y = nullptr;              // rows words
-    bool y_busy = false;                  // an asynchronous download of d_y may still be running
+    // y is double buffered too: the launch that follows a deferred download drains into d_y[y_cur], the
+    // copy engine reads that buffer out, and later launches drain into the other one
+    uint32_t *d_y[2] = {nullptr, nullptr}; // rows words each
+    int y_cur = 0;                        // THE result vector: every drain writes d_y[y_cur]
+    bool y_busy[2] = {false, false};      // an asynchronous download of d_y[b] may still be running
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_h2d_b = nullptr;       // flag pipeline: uploads alternate between two streams, so that one copy runs while the other
+                                          // stream is still busy with its flag write (a stream memory operation takes ~5 us there)
     cudaEvent_t ev_xready = nullptr, ev_xfree[2] = {nullptr, nullptr}, ev_yready = nullptr, ev_ydone = nullptr;
-    // rows + 1 accumulators (uint64 fixed / fp32 float) x 2: a launch adds into one buffer while it
-    // drains the other (the previous launch's sums) into y
-    void *d_acc[2] = {nullptr, nullptr};
+    // flag pipeline (see load_memops): sequence flags in device memory instead of events
+    bool flags_mode = false;
+    uint32_t *d_flags = nullptr;          // kNumFlags words
+    uint32_t launch_seq = 0;              // SpMV launches so far; launch n publishes n - 1 in done_seq when it starts
+    uint32_t publish_sure = 0;            // highest sequence number that WILL appear in done_seq without further host action
+    uint32_t d2h_wait_seq = 0;            // highest sequence number the download stream has been told to wait for
+    bool xwait_once = true;               // stop polling the x flag once a launch that polled it has completed
+    bool host_drain = true;               // deferred downloads into page-locked memory are written by the drain itself
+    uint32_t x_reader_seq[kXBuffers] = {0, 0, 0, 0};   // last launch that reads d_x[b]
+    // done_seq lives in mapped page-locked host memory: kernels / stream memory operations write it through
+    // d_done, the host polls h_done directly (upload throttling) instead of queueing a stream wait
+    volatile uint32_t *h_done = nullptr;
+    uint32_t *d_done = nullptr;
+    uint32_t x_seq = 0;                   // uploads so far == value written to x_ready[b] when the copy has landed
+    int x_wait_buf = -1;                  // buffer whose x_ready flag the next launches wait for (-1: none)
+    uint32_t x_wait_launch = 0;           // first launch that polled the current flag (0: none yet)
+    uint32_t x_wait_val = 0;
+    uint32_t dl_seq = 0, y_dl_seq[2] = {0, 0};   // downloads so far; value y_free[b] reaches when d_y[b] has been read out
+    // deferred download; dev != null: `host` is page-locked and mapped, the next launch drains straight into it
+    struct { void *host = nullptr; uint32_t *dev = nullptr; unsigned n = 0; bool active = false; } pending_dl;
+    const void *pin_cache_host[4] = {nullptr, nullptr, nullptr, nullptr};   // small cache of cudaPointerGetAttributes results
+    uint32_t *pin_cache_dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned pin_cache_next = 0;
+    // rows + 1 accumulators (uint64 fixed / fp32 float) x 4 in rotation: launch n adds into buffer n % 4 and,
+    // at its very end, drains buffer (n - 1) % 4 (its predecessor's sums) into y and re-zeroes it. Four, because
+    // consecutive launches overlap freely (see the kernel): buffer n % 4 is reused by launch n + 4, which
+    // checks that launch n + 1 -- the one that re-zeroed it -- is complete.
+    void *d_acc[kAccBuffers] = {nullptr, nullptr, nullptr, nullptr};
     int acc_cur = 0;
     bool drain_pending = false;           // d_acc[acc_cur ^ 1] holds sums that are not in y yet
     uint32_t drain_begin = 0, drain_end = 0;
     unsigned long long *d_trace = nullptr; // optional per-warp clock stamps of the last launch
+    unsigned long long *d_timeline = nullptr;   // optional [256][8] globaltimer stamps of the last 256 launches
     uint64_t launches = 0;
     double preprocess_s = 0;
 };
@@ -95,17 +162,22 @@ namespace {
 void free_matrix(hsb_ctx *c) {
     for (auto &m : c->mats) m.release();
     c->mats.clear();
-    cudaFree(c->d_x[0]); cudaFree(c->d_x[1]); cudaFree(c->d_y); cudaFree(c->d_acc[0]); cudaFree(c->d_acc[1]); cudaFree(c->d_cta_seg); cudaFree(c->d_segs);
-    c->d_x[0] = c->d_x[1] = nullptr; c->d_y = nullptr; c->x_latest = 0; c->x_dirty = false; c->y_busy = false; c->d_acc[0] = c->d_acc[1] = nullptr; c->d_cta_seg = nullptr; c->d_segs = nullptr;
+    for (int b = 0; b < kXBuffers; b++) { cudaFree(c->d_x[b]); c->d_x[b] = nullptr; c->x_reader_seq[b] = 0; }
+    for (int b = 0; b < kAccBuffers; b++) { cudaFree(c->d_acc[b]); c->d_acc[b] = nullptr; }
+    cudaFree(c->d_y[0]); cudaFree(c->d_y[1]); cudaFree(c->d_cta_seg); cudaFree(c->d_segs);
+    c->d_y[0] = c->d_y[1] = nullptr; c->x_latest = 0; c->x_dirty = false; c->d_cta_seg = nullptr; c->d_segs = nullptr;
+    c->y_cur = 0; c->y_busy[0] = c->y_busy[1] = false; c->pending_dl.active = false;
+    c->x_wait_buf = -1;
     c->drain_pending = false; c->acc_cur = 0;
     c->have_matrix = false;
 }
 
 int install_matrix(hsb_ctx *c, const hsb::TiledMatrix &M, const DeviceMatrix &d, size_t n_elems, size_t n_slices);
+int quiesce(hsb_ctx *c);
 
 int upload_tiled(hsb_ctx *c, const hsb::TiledMatrix &M) {
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    { int rc = quiesce(c); if (rc) return rc; }
     free_matrix(c);
     DeviceMatrix d;
     CUDA_TRY(cudaMalloc(&d.vals, M.vals.size() * 4 + 16));
@@ -166,15 +238,17 @@ int install_matrix(hsb_ctx *c, const hsb::TiledMatrix &M, const DeviceMatrix &d,
     CUDA_TRY(cudaMemcpyAsync(c->d_segs, segs.data(), segs.size() * sizeof(hsb::Segment), cudaMemcpyHostToDevice, c->stream));
     // x is padded to whole tiles so that every bulk copy of a tile stays inside the buffer
     c->x_words = M.n_col_tiles * M.tile_cols;
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < kXBuffers; b++) {
         CUDA_TRY(cudaMalloc(&c->d_x[b], (size_t)c->x_words * 4 + 16));
         CUDA_TRY(cudaMemsetAsync(c->d_x[b], 0, (size_t)c->x_words * 4, c->stream));
-        CUDA_TRY(cudaEventRecord(c->ev_xfree[b], c->stream));
+        if (b < 2) CUDA_TRY(cudaEventRecord(c->ev_xfree[b], c->stream));
     }
-    CUDA_TRY(cudaMalloc(&c->d_y, (size_t)std::max(c->rows, 1u) * 4));
-    CUDA_TRY(cudaMemsetAsync(c->d_y, 0, (size_t)std::max(c->rows, 1u) * 4, c->stream));
-    const size_t esz = c->arith == hsb::kArithFixed ? 8 : 4;
     for (int b = 0; b < 2; b++) {
+        CUDA_TRY(cudaMalloc(&c->d_y[b], (size_t)std::max(c->rows, 1u) * 4));
+        CUDA_TRY(cudaMemsetAsync(c->d_y[b], 0, (size_t)std::max(c->rows, 1u) * 4, c->stream));
+    }
+    const size_t esz = c->arith == hsb::kArithFixed ? 8 : 4;
+    for (int b = 0; b < kAccBuffers; b++) {
         CUDA_TRY(cudaMalloc(&c->d_acc[b], ((size_t)c->rows + 1) * esz));
         CUDA_TRY(cudaMemsetAsync(c->d_acc[b], 0, ((size_t)c->rows + 1) * esz, c->stream));
     }
@@ -188,51 +262,167 @@ int install_matrix(hsb_ctx *c, const hsb::TiledMatrix &M, const DeviceMatrix &d,
     return HSB_OK;
 }
 
+int finish(hsb_ctx *c);
+
+// device alias of a page-locked, mapped host buffer (hsb_host_alloc), or null for pageable memory
+uint32_t *mapped_alias(hsb_ctx *c, const void *host) {
+    for (int i = 0; i < 4; i++)
+        if (c->pin_cache_host[i] == host) return c->pin_cache_dev[i];
+    cudaPointerAttributes at;
+    uint32_t *dev = nullptr;
+    if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost) dev = (uint32_t *)at.devicePointer;
+    else cudaGetLastError();
+    const unsigned slot = c->pin_cache_next++ & 3u;
+    c->pin_cache_host[slot] = host; c->pin_cache_dev[slot] = dev;
+    return dev;
+}
+
+// A launch's completion is normally announced by its successor's prologue. When there may be no
+// successor (hsb_sync, a second upload in a row, ...) the compute stream announces everything launched
+// so far itself, with a stream memory operation behind the last kernel.
+int publish_done(hsb_ctx *c) {
+    if (c->publish_sure == c->launch_seq) return HSB_OK;
+    MEMOP_TRY(g_write32((CUstream)c->stream, (CUdeviceptr)c->d_done, c->launch_seq, 0));
+    c->publish_sure = c->launch_seq;
+    return HSB_OK;
+}
+
+// start the device -> host copy of the result vector; y is final on the compute stream in stream order
+int issue_copy_after_main(hsb_ctx *c, void *host, unsigned n) {
+    const int b = c->y_cur;
+    CUDA_TRY(cudaEventRecord(c->ev_yready, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->ev_yready, 0));
+    CUDA_TRY(cudaMemcpyAsync(host, c->d_y[b], (size_t)n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    if (c->flags_mode) {
+        c->y_dl_seq[b] = ++c->dl_seq;
+        MEMOP_TRY(g_write32((CUstream)c->s_d2h, (CUdeviceptr)(c->d_flags + kFlagYFree + b), c->y_dl_seq[b], 0));
+    } else {
+        CUDA_TRY(cudaEventRecord(c->ev_ydone, c->s_d2h));
+    }
+    c->y_busy[b] = true;
+    return HSB_OK;
+}
+
 // one launch = one SpMV over the slices of `slot` (0: whole matrix, 1 + j: row partition j), rows [rb, re)
 int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, cudaEvent_t k1) {
+    // a deferred download rides on a whole-matrix launch only (its successor's drain then rewrites every
+    // row of the other y buffer); anything else resolves it the immediate way first
+    if (c->pending_dl.active && slot != 0) { int rc = finish(c); if (rc) return rc; }
     const DeviceMatrix &m = c->mats[c->next_replica % c->mats.size()];
     c->next_replica++;
     const uint32_t G = (uint32_t)c->sm_count;
     const int grid = (int)c->plan_grid[slot];
     hsb::SpmvParams p;
+    std::memset(&p, 0, sizeof p);
     p.vals = m.vals; p.cols = m.cols; p.slice_rows = m.slice_rows;
     p.cta_seg = c->d_cta_seg + slot * (size_t)(G + 1);
     p.segs = c->d_segs;
-    if (c->x_dirty) {                                   // the vector this launch reads is still being uploaded
-        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_xready, 0));
-        c->x_dirty = false;
+    const int yb = c->y_cur;
+    if (c->flags_mode) {
+        // nothing but the launch goes on the compute stream: the kernel itself waits for its x (a flag the
+        // upload stream writes after the copy) and, before its prologue drain overwrites y, for the
+        // download that still reads it
+        // every launch that may start before the upload has landed polls its flag; once a launch that
+        // polled is known to be complete (the host-visible done_seq) the vector is there for good
+        if (c->x_wait_buf >= 0 && c->xwait_once && c->x_wait_launch && (int32_t)(*c->h_done - c->x_wait_launch) >= 0)
+            c->x_wait_buf = -1;
+        if (c->x_wait_buf >= 0) {
+            p.wait_x_flag = c->d_flags + kFlagXReady + c->x_wait_buf; p.wait_x_val = c->x_wait_val;
+            if (!c->x_wait_launch) c->x_wait_launch = c->launch_seq + 1;
+        }
+        if (c->drain_pending && c->y_busy[yb]) {
+            p.wait_y_flag = c->d_flags + kFlagYFree + yb; p.wait_y_val = c->y_dl_seq[yb];
+            c->y_busy[yb] = false;                         // later writers are ordered behind this launch
+        }
+        p.done_seq = c->d_done;
+        c->x_reader_seq[c->x_latest] = c->launch_seq + 1;
+        c->publish_sure = std::max(c->publish_sure, c->launch_seq);
+    } else {
+        if (c->x_dirty) {                                   // the vector this launch reads is still being uploaded
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_xready, 0));
+            c->x_dirty = false;
+        }
+        if (c->drain_pending && c->y_busy[yb]) {            // the prologue drain writes y: wait for its last reader
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_ydone, 0));
+            c->y_busy[yb] = false;
+        }
     }
-    if (c->drain_pending && c->y_busy) {                // the prologue drain writes y: wait for its last reader
-        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_ydone, 0));
-        c->y_busy = false;
+    p.seq = ++c->launch_seq;
+    p.done_dev = c->d_flags + kFlagDoneDev;
+    p.error_flag = c->d_flags + kFlagError;
+    if (p.seq > 3) { p.guard_flag = p.done_dev; p.guard_val = p.seq - 3; }
+    p.x = c->d_x[c->x_latest]; p.y = c->d_y[yb];
+    if (c->pending_dl.active && c->pending_dl.dev && c->drain_pending) {
+        // page-locked destination: the prologue drain writes the result words to the host buffer as well
+        // (posted PCIe writes that trickle out under the SpMV); no copy engine, no second y buffer
+        p.y_host = c->pending_dl.dev; p.y_host_rows = c->pending_dl.n;
     }
-    p.x = c->d_x[c->x_latest]; p.y = c->d_y;
     p.acc = c->d_acc[c->acc_cur];
-    p.drain_acc = c->drain_pending ? c->d_acc[c->acc_cur ^ 1] : nullptr;
+    p.drain_acc = c->drain_pending ? c->d_acc[(c->acc_cur + kAccBuffers - 1) % kAccBuffers] : nullptr;
     p.drain_begin = c->drain_begin; p.drain_end = c->drain_end;
     p.trash_row = c->rows;
     p.trace = c->d_trace;
+    if (c->d_timeline) {
+        p.timeline = c->d_timeline;
+    }
     if (k0) CUDA_TRY(cudaEventRecord(k0, c->stream));
     CUDA_TRY(hsb::launch_spmv(c->arith, p, grid, c->smem_bytes, c->stream));
     c->launches++;
     if (k1) CUDA_TRY(cudaEventRecord(k1, c->stream));
+    if (c->pending_dl.active && !c->pending_dl.dev) {
+        // the launch just issued drains the requested result into d_y[yb]; once it has completed (its
+        // sequence number appears in done_seq) the download stream copies it out, and from now on the
+        // drains go to the other buffer
+        MEMOP_TRY(g_wait32((CUstream)c->s_d2h, (CUdeviceptr)c->d_done, p.seq, CU_STREAM_WAIT_VALUE_GEQ));
+        c->d2h_wait_seq = p.seq;
+        CUDA_TRY(cudaMemcpyAsync(c->pending_dl.host, c->d_y[yb], (size_t)c->pending_dl.n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        c->y_dl_seq[yb] = ++c->dl_seq;
+        MEMOP_TRY(g_write32((CUstream)c->s_d2h, (CUdeviceptr)(c->d_flags + kFlagYFree + yb), c->y_dl_seq[yb], 0));
+        c->y_busy[yb] = true;
+        c->y_cur ^= 1;
+    }
+    c->pending_dl.active = false;                           // (a mapped host buffer was handed to the launch itself)
     c->drain_pending = true;
     c->drain_begin = rb; c->drain_end = re;
-    c->acc_cur ^= 1;
+    c->acc_cur = (c->acc_cur + 1) % kAccBuffers;
     return HSB_OK;
 }
 
-// make y final: drain what the last launch accumulated (stream-ordered, no host sync)
+// make y final: drain what the last launch accumulated (stream-ordered, no host sync), and start a
+// deferred download if one is waiting
 int finish(hsb_ctx *c) {
-    if (!c->drain_pending) return HSB_OK;
-    if (c->y_busy) {
-        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_ydone, 0));
-        c->y_busy = false;
+    if (c->drain_pending) {
+        const int yb = c->y_cur;
+        if (c->y_busy[yb]) {
+            if (c->flags_mode)
+                MEMOP_TRY(g_wait32((CUstream)c->stream, (CUdeviceptr)(c->d_flags + kFlagYFree + yb), c->y_dl_seq[yb],
+                                   CU_STREAM_WAIT_VALUE_GEQ));   // (off the fast path)
+            else
+                CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_ydone, 0));
+            c->y_busy[yb] = false;
+        }
+        CUDA_TRY(hsb::launch_drain(c->arith, c->d_acc[(c->acc_cur + kAccBuffers - 1) % kAccBuffers], c->d_y[yb], c->drain_begin, c->drain_end, c->rows,
+                                   c->stream));
+        c->launches++;
+        c->drain_pending = false;
     }
-    CUDA_TRY(hsb::launch_drain(c->arith, c->d_acc[c->acc_cur ^ 1], c->d_y, c->drain_begin, c->drain_end, c->rows,
-                               c->stream));
-    c->launches++;
-    c->drain_pending = false;
+    // the download stream may be parked on the last launch's number, which only a successor would announce
+    if (c->flags_mode && c->d2h_wait_seq > c->publish_sure) { int rc = publish_done(c); if (rc) return rc; }
+    if (c->pending_dl.active) {
+        c->pending_dl.active = false;
+        return issue_copy_after_main(c, c->pending_dl.host, c->pending_dl.n);
+    }
+    return HSB_OK;
+}
+
+// every stream idle, nothing deferred: the state in which buffers may be freed or replaced
+int quiesce(hsb_ctx *c) {
+    if (c->have_matrix) { int rc = finish(c); if (rc) return rc; }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->s_h2d));
+    CUDA_TRY(cudaStreamSynchronize(c->s_h2d_b));
+    CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
+    c->y_busy[0] = c->y_busy[1] = false;
     return HSB_OK;
 }
 
@@ -287,11 +477,21 @@ hsb_ctx *hsb_create(int device, int impl) {
     }
     c->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_h2d_b, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
     cudaEvent_t *evs[] = {&c->ev_xready, &c->ev_xfree[0], &c->ev_xfree[1], &c->ev_yready, &c->ev_ydone};
     for (cudaEvent_t *ev : evs)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = hsb::configure_kernels();
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_flags, kNumFlags * 4);
+    if (e == cudaSuccess) e = cudaMemset(c->d_flags, 0, kNumFlags * 4);
+    if (e == cudaSuccess && load_memops()) {
+        void *hd = nullptr;
+        if (e == cudaSuccess) e = cudaHostAlloc(&hd, 64, cudaHostAllocMapped);
+        if (e == cudaSuccess) { std::memset(hd, 0, 64); c->h_done = (volatile uint32_t *)hd; }
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&c->d_done, hd, 0);
+        c->flags_mode = e == cudaSuccess;
+    }
     if (e != cudaSuccess) {
         set_err(HSB_ECUDA, std::string("kernel configuration failed: ") + cudaGetErrorString(e));
         cudaStreamDestroy(c->stream);
@@ -304,14 +504,16 @@ hsb_ctx *hsb_create(int device, int impl) {
 void hsb_destroy(hsb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    cudaStreamSynchronize(c->s_h2d);
-    cudaStreamSynchronize(c->s_d2h);
+    quiesce(c);
     free_matrix(c);
     cudaFree(c->d_trace);
+    cudaFree(c->d_timeline);
+    cudaFree(c->d_flags);
+    if (c->h_done) cudaFreeHost((void *)c->h_done);
     cudaEvent_t evs[] = {c->ev_xready, c->ev_xfree[0], c->ev_xfree[1], c->ev_yready, c->ev_ydone};
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->s_h2d);
+    cudaStreamDestroy(c->s_h2d_b);
     cudaStreamDestroy(c->s_d2h);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -344,7 +546,7 @@ int hsb_upload_matrix_csr_device(hsb_ctx *c, uint32_t rows, uint32_t cols, uint6
                                  const uint32_t *d_indices, const void *d_vals, uint32_t rows_per_partition) {
     if (!c || !d_indptr || (nnz && (!d_indices || !d_vals))) return set_err(HSB_EINVAL, "null argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    { int rc = quiesce(c); if (rc) return rc; }
     auto t0 = std::chrono::steady_clock::now();
     free_matrix(c);
     hsb::TiledMatrix M;
@@ -440,6 +642,30 @@ int hsb_upload_vector(hsb_ctx *c, const void *x_packed, unsigned num_cols) {
     CUDA_TRY(cudaSetDevice(c->device));
     // write the buffer no in-flight launch reads: its last readers were launched before the previous
     // upload, which is when ev_xfree[b] was recorded on the compute stream
+    if (c->flags_mode) {
+        // Three buffers in rotation: this one was last read two launches ago. Instead of queueing a
+        // stream wait (a stream memory operation costs ~3 us on the copy stream) the host looks at
+        // done_seq itself -- in steady state the number is already there -- and then queues the copy and
+        // the flag that tells the next launch its x has landed.
+        const int b = (c->x_latest + 1) % kXBuffers;
+        const uint32_t need = c->x_reader_seq[b];
+        if (need) {
+            if (need > c->publish_sure) { int rc = publish_done(c); if (rc) return rc; }
+            const auto t0 = std::chrono::steady_clock::now();
+            for (unsigned spins = 0; (int32_t)(*c->h_done - need) < 0; spins++)
+                if ((spins & 0xFFFu) == 0xFFFu &&
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0)
+                    return set_err(HSB_ECUDA, "timed out waiting for the launch that still reads the x buffer");
+        }
+        cudaStream_t up = (c->x_seq & 1u) ? c->s_h2d_b : c->s_h2d;
+        CUDA_TRY(cudaMemcpyAsync(c->d_x[b], x_packed, (size_t)num_cols * 4, cudaMemcpyHostToDevice, up));
+        c->x_wait_val = ++c->x_seq;
+        c->x_wait_buf = b;
+        c->x_wait_launch = 0;
+        MEMOP_TRY(g_write32((CUstream)up, (CUdeviceptr)(c->d_flags + kFlagXReady + b), c->x_wait_val, 0));
+        c->x_latest = b;
+        return HSB_OK;
+    }
     const int b = c->x_latest ^ 1;
     CUDA_TRY(cudaStreamWaitEvent(c->s_h2d, c->ev_xfree[b], 0));
     CUDA_TRY(cudaMemcpyAsync(c->d_x[b], x_packed, (size_t)num_cols * 4, cudaMemcpyHostToDevice, c->s_h2d));
@@ -477,9 +703,18 @@ int hsb_sync(hsb_ctx *c) {
     CUDA_TRY(cudaSetDevice(c->device));
     if (c->have_matrix) { int rc = finish(c); if (rc) return rc; }
     CUDA_TRY(cudaStreamSynchronize(c->s_h2d));
+    CUDA_TRY(cudaStreamSynchronize(c->s_h2d_b));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
-    c->y_busy = false;
+    c->y_busy[0] = c->y_busy[1] = false;
+    if (c->flags_mode) {
+        uint32_t err = 0;
+        CUDA_TRY(cudaMemcpy(&err, c->d_flags + kFlagError, 4, cudaMemcpyDeviceToHost));
+        if (err) {
+            CUDA_TRY(cudaMemset(c->d_flags + kFlagError, 0, 4));
+            return set_err(HSB_ECUDA, "a kernel gave up waiting for a vector upload / result download flag");
+        }
+    }
     return HSB_OK;
 }
 
@@ -488,20 +723,29 @@ int hsb_download_result_async(hsb_ctx *c, void *y_packed, unsigned num_rows) {
     if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
     if (num_rows > c->rows) return set_err(HSB_EINVAL, "num_rows exceeds the matrix");
     CUDA_TRY(cudaSetDevice(c->device));
+    if (c->pending_dl.active) { int rc = finish(c); if (rc) return rc; }
+    // (pageable destinations are never deferred: cudaMemcpyAsync into pageable memory blocks the calling
+    // thread until the copy has run, and a deferred copy waits for a launch this thread has yet to issue)
+    uint32_t *alias = c->flags_mode && c->drain_pending ? mapped_alias(c, y_packed) : nullptr;
+    if (alias && c->drain_begin == 0 && c->drain_end == c->rows) {
+        // Deferred: the sums of the last SpMV are still in the row accumulators. The next whole-matrix
+        // hsb_spmv drains them in its prologue anyway; the copy is attached to that launch (run_slot), or
+        // issued behind an explicit drain by hsb_sync / the blocking download, whichever comes first.
+        c->pending_dl.host = y_packed; c->pending_dl.n = num_rows; c->pending_dl.active = true;
+        c->pending_dl.dev = c->host_drain ? alias : nullptr;
+        return HSB_OK;
+    }
     { int rc = finish(c); if (rc) return rc; }
-    CUDA_TRY(cudaEventRecord(c->ev_yready, c->stream));
-    CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->ev_yready, 0));
-    CUDA_TRY(cudaMemcpyAsync(y_packed, c->d_y, (size_t)num_rows * 4, cudaMemcpyDeviceToHost, c->s_d2h));
-    CUDA_TRY(cudaEventRecord(c->ev_ydone, c->s_d2h));
-    c->y_busy = true;
-    return HSB_OK;
+    return issue_copy_after_main(c, y_packed, num_rows);
 }
 
 int hsb_download_result(hsb_ctx *c, void *y_packed, unsigned num_rows) {
     int rc = hsb_download_result_async(c, y_packed, num_rows);
     if (rc) return rc;
+    rc = finish(c);                                       // a deferred copy is issued now
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
-    c->y_busy = false;
+    c->y_busy[0] = c->y_busy[1] = false;
     return HSB_OK;
 }
 
@@ -605,6 +849,72 @@ int hsb_time_spmv(hsb_ctx *c, int warmup, int steps, float *step_ms, float *kern
     return HSB_OK;
 }
 
+int hsb_time_e2e(hsb_ctx *c, const void *const x_host[2], void *const y_host[2], unsigned num_cols, unsigned num_rows,
+                 int iters, int async_download, double *seconds_per_spmv) {
+    if (!c || !x_host || !y_host || !x_host[0] || !x_host[1] || !y_host[0] || !y_host[1] || iters < 1 || !seconds_per_spmv)
+        return set_err(HSB_EINVAL, "bad argument");
+    int rc = hsb_sync(c);
+    if (rc) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int k = 0; k < iters; k++) {
+        if ((rc = hsb_upload_vector(c, x_host[k & 1], num_cols))) return rc;
+        if ((rc = hsb_spmv(c))) return rc;
+        rc = async_download ? hsb_download_result_async(c, y_host[k & 1], num_rows)
+                            : hsb_download_result(c, y_host[k & 1], num_rows);
+        if (rc) return rc;
+    }
+    if ((rc = hsb_sync(c))) return rc;
+    *seconds_per_spmv = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / iters;
+    return HSB_OK;
+}
+
+int hsb_set_option(hsb_ctx *c, const char *name, int value) {
+    if (!c || !name) return set_err(HSB_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    { int rc = quiesce(c); if (rc) return rc; }
+    const std::string n(name);
+    if (n == "flags") {                 // 0: events between launches (the pre-pipeline behaviour), 1: flag pipeline
+        if (value && !c->d_done) return set_err(HSB_ESTATE, "stream memory operations are not available");
+        c->flags_mode = value != 0;
+        if (!c->flags_mode && c->x_latest > 1 && c->have_matrix) {      // event mode rotates buffers 0 and 1 only
+            CUDA_TRY(cudaMemcpy(c->d_x[0], c->d_x[c->x_latest], (size_t)c->x_words * 4, cudaMemcpyDeviceToDevice));
+            c->x_latest = 0;
+        }
+        c->x_wait_buf = -1; c->x_dirty = false;
+        for (int b = 0; b < kXBuffers; b++) c->x_reader_seq[b] = 0;
+        for (int b = 0; b < 2; b++) CUDA_TRY(cudaEventRecord(c->ev_xfree[b], c->stream));
+    } else if (n == "xwait_once") {
+        c->xwait_once = value != 0;
+    } else if (n == "host_drain") {
+        c->host_drain = value != 0;
+    } else {
+        return set_err(HSB_EINVAL, "unknown option: " + n);
+    }
+    return HSB_OK;
+}
+
+int hsb_debug_timeline(hsb_ctx *c, unsigned long long *out, size_t capacity) {
+    if (!c) return set_err(HSB_EINVAL, "null context");
+    const size_t n = 256 * 8;
+    CUDA_TRY(cudaSetDevice(c->device));
+    { int rc = quiesce(c); if (rc) return rc; }
+    if (!out) {
+        if (capacity) {                            // (re-)arm: covers the next 256 launches
+            if (!c->d_timeline) CUDA_TRY(cudaMalloc(&c->d_timeline, n * 8));
+            std::vector<unsigned long long> init(n, 0);
+            for (size_t i = 0; i < n; i += 8) init[i] = ~0ull;
+            CUDA_TRY(cudaMemcpy(c->d_timeline, init.data(), n * 8, cudaMemcpyHostToDevice));
+        } else if (!capacity && c->d_timeline) {
+            cudaFree(c->d_timeline);
+            c->d_timeline = nullptr;
+        }
+        return (int)n;
+    }
+    if (!c->d_timeline || capacity < n) return set_err(HSB_ESTATE, "timeline not armed or buffer too small");
+    CUDA_TRY(cudaMemcpy(out, c->d_timeline, n * 8, cudaMemcpyDeviceToHost));
+    return (int)(c->launch_seq & 0x7FFFFFFF);
+}
+
 int hsb_debug_trace(hsb_ctx *c, unsigned long long *out, size_t capacity) {
     if (!c) return set_err(HSB_EINVAL, "null context");
     const size_t n = (size_t)c->sm_count * (hsb::kWarps + 2);
@@ -650,7 +960,7 @@ int hsb_debug_plan(hsb_ctx *c, uint32_t *steps, uint32_t *slices, size_t capacit
 }
 
 void *hsb_device_x(hsb_ctx *c) { return c ? c->d_x[c->x_latest] : nullptr; }
-void *hsb_device_y(hsb_ctx *c) { return c ? c->d_y : nullptr; }
+void *hsb_device_y(hsb_ctx *c) { return c ? c->d_y[c->y_cur] : nullptr; }
 void *hsb_stream(hsb_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 }  // extern "C"

@@ -48,6 +48,24 @@ __device__ __forceinline__ uint2 ldg_stream64(const uint2 *p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
+// Bounded spin on a sequence flag another engine writes (a stream memory operation on a copy stream):
+// true once (int)(flag - val) >= 0. About a quarter of a second worth of polls, then give up rather than hang the GPU.
+__device__ __forceinline__ unsigned long long globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool wait_flag_geq(const uint32_t *flag, uint32_t val) {
+    for (uint32_t i = 0; i < (1u << 18); i++) {
+        uint32_t v;
+        // relaxed: what is read afterwards (x through the TMA / async proxy, which does not go through L1) was
+        // written to device memory by the copy engine before the flag; an acquire here costs ~3 us per launch
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - val) >= 0) return true;
+        __nanosleep(i < 64 ? 100 : 1000);
+    }
+    return false;
+}
 // ---------------------------------------------------------------------------------------
 // arithmetic policies
 // ---------------------------------------------------------------------------------------
@@ -165,18 +183,23 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, uint64_t *bar,
     vp += kPrefetch * kLanes;
     cp += kPrefetch * kLanes;
 
-    uint32_t sl = 0, left = 0, row = 0, row_next = 0;
+    // row ids of the current slice and of the next kRowAhead slices (short slices -- hypersparse tiles --
+    // finish every step or two, so one slice of look-ahead would expose the load latency)
+    uint32_t sl = 0, left = 0, row = 0, row_next[kRowAhead] = {};
     const uint32_t *rp = p.slice_rows;
     if (remaining) {
         sl = first_slice;                                     // the slice that contains step ta (host plan)
         left = steps_before(cnt, sl + 1) - ta;                // steps of slice sl still ahead of us
         rp = p.slice_rows + (size_t)(slice_begin + sl) * kLanes + lane;
         row = __ldg(rp);
-        if (sl + 1 < n_slices) row_next = __ldg(rp + kLanes);
+#pragma unroll
+        for (int a = 0; a < kRowAhead; a++)
+            if (sl + 1 + a < n_slices) row_next[a] = __ldg(rp + (1 + a) * kLanes);
     }
 
-    if (first_segment) before_x_wait();                      // previous launch complete; drain its sums
+    if (first_segment) before_x_wait();                      // the accumulator buffer is ours (see the kernel)
     mbar_wait(bar, parity);
+    if (p.timeline && first_segment && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[(size_t)(p.seq & 255u) * 8 + 4] = globaltimer();
     if (!remaining) return;
 
     uint32_t xs_base = smem_u32(xs);
@@ -201,9 +224,12 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, uint64_t *bar,
             acc.clear();
             sl++;
             rp += kLanes;
-            row = row_next;
-            if (sl + 1 < n_slices) row_next = __ldg(rp + kLanes);
-            if (sl + 8 < n_slices && lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 8 * kLanes));
+            row = row_next[0];
+#pragma unroll
+            for (int a = 0; a + 1 < kRowAhead; a++) row_next[a] = row_next[a + 1];
+            if (sl + kRowAhead < n_slices) row_next[kRowAhead - 1] = __ldg(rp + kRowAhead * kLanes);
+            if (sl + 8 + kRowAhead < n_slices && lane == 0)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (8 + kRowAhead) * kLanes));
             left = steps_of(cnt, sl);
         }
     };
@@ -239,25 +265,27 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_tiles_kernel(const SpmvParam
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t g0 = __ldg(p.cta_seg + blockIdx.x), g1 = __ldg(p.cta_seg + blockIdx.x + 1);
     const long long t_start = clock64();
+    unsigned long long *tl = p.timeline ? p.timeline + (size_t)(p.seq & 255u) * 8 : nullptr;
+    if (tl && tid == 0) atomicMin(tl + 0, globaltimer());
 
-    // Drain the previous launch's accumulators (clamp / copy into y, re-zero): the pe dump + result
-    // drain of the reference (pe.h:95-116, spmv_result_drain.cpp) and the PE's reset loop
-    // (pe.h:131-135). The previous launch is complete once griddepcontrol.wait returns, and this
-    // launch accumulates into the other buffer, so the drain overlaps the x staging.
-    auto drain = [&]() {
-        if (p.drain_acc) {
-            for (uint32_t r = p.drain_begin + blockIdx.x * kThreads + tid; r < p.drain_end; r += gridDim.x * kThreads)
-                p.y[r] = A::drain(p.drain_acc, r);
-            if (blockIdx.x == 0 && tid == 0) (void)A::drain(p.drain_acc, p.trash_row);
+    // Programmatic dependent launch, both ways round. (1) The successor may start as early as it finds a
+    // free SM: nothing this launch still has to do can be disturbed by it (it accumulates into another
+    // buffer, reads another x). (2) This launch does not wait for its predecessor before working either:
+    // only the DRAIN of the predecessor's row sums needs the predecessor complete, so the
+    // griddepcontrol.wait sits at the very end of the CTA, where it returns at once. (Waiting at the start
+    // costs 3.6 us per launch in a device-resident loop and up to 10 us when PCIe copies are in flight:
+    // the grid-completion flush the wait includes is slowed down by them -- measured with the
+    // %globaltimer timeline.)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    // The accumulator buffer of this launch was last used four launches ago and re-zeroed by the drain at
+    // the end of launch seq-3. In the steady state that launch is long gone; the guard only ever spins when
+    // several small launches are resident at once.
+    auto guard = [&]() {
+        if (p.guard_flag) {
+            if (lane == 0 && !wait_flag_geq(p.guard_flag, p.guard_val)) atomicExch(p.error_flag, 1u);
+            __syncwarp();
         }
-    };
-    // Programmatic dependent launch: everything above the wait (work-plan loads, x staging, the
-    // first matrix loads) only reads data no kernel writes, so it runs while the previous launch's
-    // slower CTAs are still finishing on other SMs.
-    auto wait_for_previous_launch = [&]() {
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        drain();
     };
 
     if (g0 < g1) {
@@ -274,6 +302,8 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_tiles_kernel(const SpmvParam
             const uint32_t cnt = __ldg(&sg->cnt_ge[lane]);
             // stage the x tile: the vector loader + vecbuf writer of the reference
             if (tid == 0) {
+                if (g == g0 && p.wait_x_flag && !wait_flag_geq(p.wait_x_flag, p.wait_x_val)) atomicExch(p.error_flag, 1u);
+                if (tl && blockIdx.x == 0 && g == g0) tl[1] = globaltimer();
                 fence_proxy_async();
                 const uint32_t bytes = h1.x * 4u;
                 mbar_arrive_expect_tx(&bar, bytes);
@@ -284,16 +314,40 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_tiles_kernel(const SpmvParam
             // this warp's equal-cost share of the segment (host plan)
             const uint32_t ta = __ldg(&sg->warp_t[warp]), tb = __ldg(&sg->warp_t[warp + 1]);
             const uint32_t first_slice = __ldg(&sg->warp_slice[warp]);
-            stream_steps<A>(p, &bar, parity, cnt, h1.y, h1.z, h1.w, ta, tb, first_slice, lane, g == g0,
-                            wait_for_previous_launch);
+            stream_steps<A>(p, &bar, parity, cnt, h1.y, h1.z, h1.w, ta, tb, first_slice, lane, g == g0, guard);
             parity ^= 1u;
             if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * (kWarps + 2) + warp] = clock64() - t_start;
             __syncthreads();                                       // everyone is done with this x tile
         }
-    } else {
-        wait_for_previous_launch();
+    }
+    if (tl && blockIdx.x == 0 && tid == 0) tl[6] = globaltimer();
+
+    // Drain the predecessor's accumulators (clamp / copy into y, re-zero): the pe dump + result drain of
+    // the reference (pe.h:95-116, spmv_result_drain.cpp) and the PE's reset loop (pe.h:131-135).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tl && blockIdx.x == 0 && tid == 0) tl[2] = globaltimer();
+    if (p.drain_acc) {
+        if (p.wait_y_flag) {                                     // y is still being copied to the host
+            if (lane == 0 && !wait_flag_geq(p.wait_y_flag, p.wait_y_val)) atomicExch(p.error_flag, 1u);
+            __syncwarp();
+        }
+        for (uint32_t r = p.drain_begin + blockIdx.x * kThreads + tid; r < p.drain_end; r += gridDim.x * kThreads) {
+            const uint32_t v = A::drain(p.drain_acc, r);
+            p.y[r] = v;
+            if (p.y_host && r < p.y_host_rows) __stcs(p.y_host + r, v);        // posted write over PCIe
+        }
+        if (blockIdx.x == 0 && tid == 0) (void)A::drain(p.drain_acc, p.trash_row);
+    }
+    // The predecessor is complete and its writes are visible: announce it -- to later launches (guard), to
+    // the host (upload throttling reads the mapped copy) and to the copy streams (cuStreamWaitValue32).
+    // Relaxed stores: griddepcontrol.wait has already ordered the predecessor's writes.
+    if (blockIdx.x == 0 && tid == 0) {
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.done_dev), "r"(p.seq - 1u) : "memory");
+        if (p.done_seq) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.done_seq), "r"(p.seq - 1u) : "memory");
+        if (tl) tl[3] = globaltimer();
     }
     if (p.trace && tid == 0) p.trace[(size_t)blockIdx.x * (kWarps + 2) + kWarps] = clock64() - t_start;
+    if (tl && tid == 0) atomicMax(tl + 5, globaltimer());
 }
 
 template <class A>

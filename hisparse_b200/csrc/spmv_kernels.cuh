@@ -49,6 +49,10 @@ constexpr uint32_t kBulkPiece = 16384;               // bytes per cp.async.bulk
 #define HSB_PREFETCH 4
 #endif
 constexpr int kPrefetch = HSB_PREFETCH;              // slice steps in flight per warp
+#ifndef HSB_ROW_AHEAD
+#define HSB_ROW_AHEAD 1
+#endif
+constexpr int kRowAhead = HSB_ROW_AHEAD;             // slices whose row ids are loaded ahead of their use
 
 struct SpmvParams {
     const uint32_t *vals;
@@ -58,12 +62,30 @@ struct SpmvParams {
     const Segment *segs;          // (tile, [t_lo, t_hi) tile-relative steps, tile geometry): one x staging each
     const uint32_t *x;            // packed dense vector, raw 32-bit words
     void *acc;                    // row accumulators of THIS launch (uint64 fixed / fp32 float), rows + 1 entries,
-                                  // all zero on entry
+                                  // all zero once guard_val has been seen
     void *drain_acc;              // accumulators of the PREVIOUS launch still to be drained into y, or null
     uint32_t *y;                  // packed result, raw 32-bit words
     uint32_t drain_begin, drain_end;  // rows of drain_acc to drain
     uint32_t trash_row;           // accumulator index of unused lanes (== rows)
     unsigned long long *trace;    // optional [gridDim.x][kWarps + 2] SM-clock stamps (profiling aid), or null
+    // Flag pipeline (host <-> device overlap without stream events between launches, which would undo the
+    // programmatic-dependent-launch overlap of consecutive SpMVs). All flags are 32-bit sequence
+    // numbers in device memory, compared cyclically; null pointers switch the feature off.
+    const uint32_t *wait_x_flag;  // the copy stream writes wait_x_val here once this launch's x has landed
+    uint32_t wait_x_val;
+    const uint32_t *wait_y_flag;  // ... and wait_y_val here once the last download of `y` has been read out
+    uint32_t wait_y_val;
+    uint32_t *done_dev;           // launch `seq` publishes seq - 1 here (device memory) once its predecessor has completed ...
+    uint32_t *done_seq;           // ... and here (mapped host memory, read by the host and the copy streams), or null
+    uint32_t seq;
+    const uint32_t *guard_flag;   // == done_dev when this launch must see guard_val there before its first row update
+    uint32_t guard_val;           // (launch seq - 3 has re-zeroed the accumulator buffer), else null
+    uint32_t *error_flag;         // set to 1 if a flag wait timed out (the launch then proceeds: no hang)
+    unsigned long long *timeline; // optional [256][8] %globaltimer stamps indexed by seq % 256 (profiling aid), or null:
+                                  // 0 first CTA start, 1 CTA0 x flag seen, 2 CTA0 predecessor complete, 3 CTA0 drain done,
+                                  // 4 CTA0 x tile staged, 5 last CTA end, 6 CTA0 matrix work done
+    uint32_t *y_host;             // device alias of a mapped page-locked host buffer the drain ALSO writes (rows
+    uint32_t y_host_rows;         // < y_host_rows), or null: a download without the copy engine
 };
 
 enum { kArithFixed = 0, kArithFloat = 1 };

@@ -426,8 +426,26 @@ void plan_launch(const TiledMatrix &m, uint32_t tile_begin, uint32_t tile_end, u
         for (; b <= ctas; b++) (*cta_seg)[b] = (uint32_t)segs->size();
         return;
     }
-    // more tiles than CTAs: contiguous equal-cost split of the tile sequence; a CTA runs whole
-    // tiles and at most a partial tile at either end
+    // more tiles than CTAs: equal-cost split of the tile sequence; a CTA runs whole tiles and at most a
+    // partial tile at either end. With many tiles per CTA the sequence is first interleaved -- position
+    // b * per + k holds tile k * ctas + b -- so that at any moment the CTAs work on NEIGHBOURING tiles
+    // (the same row partition, adjacent column ranges) instead of 'ctas' far-apart regions: the row
+    // accumulators the concurrent CTAs update then form a window that stays in L2 (matrices with a
+    // diagonal band: C5), and so do the x tiles being staged.
+    static const bool interleave = [] { const char *e = std::getenv("HSB_TILE_INTERLEAVE"); return !e || std::atoi(e) != 0; }();
+    if (interleave && live.size() >= 2 * (size_t)ctas) {
+        const size_t n = live.size(), per = (n + ctas - 1) / ctas;
+        std::vector<uint32_t> l2;
+        std::vector<double> c2;
+        l2.reserve(n); c2.reserve(n);
+        for (size_t b = 0; b < ctas; b++)
+            for (size_t k = 0; k < per; k++) {
+                const size_t i = k * ctas + b;
+                if (i < n) { l2.push_back(live[i]); c2.push_back(cost[i]); }
+            }
+        live.swap(l2);
+        cost.swap(c2);
+    }
     size_t i = 0;
     uint32_t prev = 0;                 // next unassigned step of tile live[i]
     double done = 0;                   // cost of everything before tile live[i]

@@ -126,8 +126,11 @@ int hsb_sync(hsb_ctx *ctx);
  * y_packed: num_rows 32-bit words, natural row order. Synchronises. */
 int hsb_download_result(hsb_ctx *ctx, void *y_packed, unsigned num_rows);
 /* The same without the finish(): the copy runs on its own stream (the reference's queue is out of
- * order too, sw/host.cpp:586-590); y_packed is valid after the next hsb_sync(). Together with the
- * double-buffered x of hsb_upload_vector this lets upload(k+1), SpMV(k) and download(k-1) overlap. */
+ * order too, sw/host.cpp:586-590); y_packed is valid after the next hsb_sync() -- not earlier: when the
+ * sums of the last SpMV are still in the row accumulators the copy is deferred and attached to the next
+ * hsb_spmv (whose prologue drains them anyway) or issued by hsb_sync. Together with the double-buffered
+ * x of hsb_upload_vector and a double-buffered device y, upload(k+1), SpMV(k) and download(k-1)
+ * overlap, and the compute stream carries nothing but back-to-back kernel launches. */
 int hsb_download_result_async(hsb_ctx *ctx, void *y_packed, unsigned num_rows);
 
 /* == spmv_csim/csim.cpp:22-46 `top_wrapper`: one row partition, host buffers in, host buffer out.
@@ -146,17 +149,57 @@ int hsb_set_replicas(hsb_ctx *ctx, int n);
  * step_ms = (stop - start) / steps over the whole loop; kernel_ms = mean duration of the main
  * tile kernel alone, from per-launch event pairs in a second loop of the same length. */
 int hsb_time_spmv(hsb_ctx *ctx, int warmup, int steps, float *step_ms, float *kernel_ms);
+/* End-to-end timing with HOST buffers (what bench.py reports as e2e): `iters` times
+ *   hsb_upload_vector(x_host[k & 1]); hsb_spmv(); hsb_download_result[_async](y_host[k & 1]);
+ * then hsb_sync(), on the wall clock -- the loop of sw/benchmark.cpp:315-343 with the transfers
+ * inside, issued from C the way the reference's C++ benchmark issues its OpenCL calls. */
+int hsb_time_e2e(hsb_ctx *ctx, const void *const x_host[2], void *const y_host[2], unsigned num_cols,
+                 unsigned num_rows, int iters, int async_download, double *seconds_per_spmv);
+/* Tuning / A-B switches (synchronises first). "flags": 1 = flag pipeline (default when the driver offers
+ * stream memory operations), 0 = stream events between launches; "xwait_once": 1 = launches stop polling
+ * the x flag once one that polled it has completed (default); "host_drain": 1 = deferred downloads into
+ * page-locked memory are written by the kernel's drain itself instead of the copy engine (default). */
+int hsb_set_option(hsb_ctx *ctx, const char *name, int value);
 /* Profiling aid: SM-clock stamps of the last launch, [sm_count][34] = per warp "my slices are done",
  * then CTA "arrived at the grid barrier", then "drain done". out == NULL arms (capacity != 0) or
  * disarms (capacity == 0) the trace and returns the number of words. */
 int hsb_debug_trace(hsb_ctx *ctx, unsigned long long *out, size_t capacity);
+/* Profiling aid: %globaltimer stamps (ns) of the last 256 SpMV launches, [256][8] indexed by launch number
+ * % 256: 0 first CTA started, 1 CTA 0 saw its x flag, 2 CTA 0 saw the predecessor complete, 3 CTA 0 finished
+ * its drain share, 4 CTA 0 has its x tile, 5 last CTA ended. out == NULL arms (capacity != 0) / disarms.
+ * Returns the number of the last launch. */
+int hsb_debug_timeline(hsb_ctx *ctx, unsigned long long *out, size_t capacity);
 /* Profiling aid: steps and slices the whole-matrix plan gives to every CTA. */
 int hsb_debug_plan(hsb_ctx *ctx, uint32_t *steps, uint32_t *slices, size_t capacity);
 /* raw device pointers / stream for callers that move x or y with NCCL (torch.distributed);
  * call hsb_sync() before reading device y */
 void *hsb_device_x(hsb_ctx *ctx);
-void *hsb_device_y(hsb_ctx *ctx);
+void *hsb_device_y(hsb_ctx *ctx);   /* query after hsb_sync(): the result buffer alternates when downloads are deferred */
 void *hsb_stream(hsb_ctx *ctx);
+
+/* ---- synthetic matrices generated on the device (benchmark inputs; no reference counterpart: the
+ * reference loads .npz datasets, sw/data_loader.h:51-70) ------------------------------------------ */
+typedef struct hsb_device_csr {
+    uint32_t rows, cols;
+    uint64_t nnz;
+    uint32_t *d_indptr, *d_indices, *d_vals;   /* device pointers: rows + 1, nnz, nnz words */
+    int device;
+} hsb_device_csr;
+/* Rows [first_global_row, first_global_row + rows) of a power-law matrix with `cols` columns (BASELINE
+ * config C5): row degree = truncated discrete Pareto(alpha) with mean `mean_degree`, clipped to
+ * max_degree; a fraction band_fraction of a row's columns lies within +-band_half_width of the
+ * diagonal, the rest is uniform; column ids sorted and unique per row. Values U[0,1) * value_scale as
+ * fp32 bits (value_kind 0) or raw Q8.24 words (value_kind 1). A pure function of (seed, global row):
+ * shards generated on different GPUs are pieces of the same matrix. The result feeds
+ * hsb_upload_matrix_csr_device; release it with hsb_device_csr_free. */
+int hsb_synth_powerlaw_csr_device(int device, uint32_t rows, uint32_t cols, uint64_t first_global_row,
+                                  double mean_degree, double alpha, uint32_t max_degree,
+                                  uint32_t band_half_width, double band_fraction, uint64_t seed,
+                                  int value_kind, float value_scale, hsb_device_csr *out);
+/* any of indptr / indices / vals may be NULL */
+int hsb_device_csr_download(const hsb_device_csr *m, uint32_t *indptr, uint32_t *indices, uint32_t *vals);
+void hsb_device_csr_free(hsb_device_csr *m);
+const char *hsb_synth_last_error(void);
 
 /* ---- host-side format inspection (no GPU needed; used by the CPU test-suite) --------------- */
 typedef struct hsb_format hsb_format;

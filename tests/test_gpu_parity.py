@@ -146,6 +146,135 @@ def test_pipelined_upload_spmv_download(gpu, port):
 # ------------------------------------------------------------------------------------------
 # fixtures produced by the reference C simulation
 # ------------------------------------------------------------------------------------------
+
+def test_deferred_download_state_machine(gpu, port):
+    """Downloads requested right after an SpMV are deferred onto the next launch (flag pipeline, two device
+    y buffers). Every way out of the deferred state must deliver the right vector: the next whole-matrix
+    SpMV, a row-partition launch, hsb_sync, the blocking download, and a second request in a row."""
+    rows, cols, indptr, indices, data = matgen.rmat_csr(3000, 60000, 21)
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
+    words = port.quantize(data)
+    rng = np.random.default_rng(4)
+    xs = [port.quantize(rng.random(c2, dtype=np.float32)) for _ in range(6)]
+    wants = [port.spmv_q824(ip2, indices, words, x) for x in xs]
+    rpp = 1024
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, words, rpp)
+    nparts = (r2 + rpp - 1) // rpp
+    out = [capi.PinnedArray(r2) for _ in range(8)]
+
+    def all_partitions(x):
+        ctx.upload_vector(x)
+        for j in range(nparts):
+            rows_here = min(rpp, r2 - j * rpp)
+            ctx.spmv_row_partition(j, rows_here // 16, 1, nparts, c2)
+
+    # deferred -> consumed by the next whole-matrix SpMV (twice in a row) -> resolved by hsb_sync
+    for k in range(3):
+        ctx.upload_vector(xs[k]); ctx.spmv(); ctx.download_result_async(out[k].array)
+    ctx.sync()
+    for k in range(3):
+        assert np.array_equal(out[k].array, wants[k]), k
+    # the same into pageable memory (copy engine + second device y buffer instead of the drain-to-host path),
+    # and with the drain-to-host path switched off
+    pageable = [np.zeros(r2, np.uint32) for _ in range(4)]
+    for k in range(4):
+        ctx.upload_vector(xs[k]); ctx.spmv(); ctx.download_result_async(pageable[k])
+    ctx.sync()
+    for k in range(4):
+        assert np.array_equal(pageable[k], wants[k]), k
+    ctx.set_option("host_drain", 0)
+    for k in range(4):
+        ctx.upload_vector(xs[k + 1]); ctx.spmv(); ctx.download_result_async(out[k].array)
+    ctx.sync()
+    for k in range(4):
+        assert np.array_equal(out[k].array, wants[k + 1]), k
+    ctx.set_option("host_drain", 1)
+    ctx.set_option("flags", 0)
+    for k in range(4):
+        ctx.upload_vector(xs[k]); ctx.spmv(); ctx.download_result_async(out[k].array)
+    ctx.sync()
+    for k in range(4):
+        assert np.array_equal(out[k].array, wants[k]), k
+    ctx.set_option("flags", 1)
+    # deferred -> a row-partition launch comes next (immediate resolution), then the partition flow's own result
+    ctx.upload_vector(xs[3]); ctx.spmv(); ctx.download_result_async(out[3].array)
+    all_partitions(xs[4])
+    ctx.download_result_async(out[4].array)
+    ctx.sync()
+    assert np.array_equal(out[3].array, wants[3]) and np.array_equal(out[4].array, wants[4])
+    # deferred -> blocking download of the same result; two requests for one result; device y after sync
+    ctx.upload_vector(xs[5]); ctx.spmv()
+    ctx.download_result_async(out[5].array)
+    ctx.download_result_async(out[6].array)
+    y = ctx.download_result()
+    ctx.sync()
+    assert np.array_equal(y, wants[5]) and np.array_equal(out[5].array, wants[5]) and np.array_equal(out[6].array, wants[5])
+    # a long pipelined run alternating two vectors and two host buffers (what hsb_time_e2e issues)
+    px = [capi.PinnedArray(c2) for _ in range(2)]
+    px[0].array[:] = xs[0]; px[1].array[:] = xs[1]
+    sec = ctx.time_e2e([px[0].array, px[1].array], [out[0].array, out[1].array], 200, async_download=True)
+    assert sec > 0
+    assert np.array_equal(out[0].array, wants[0]) and np.array_equal(out[1].array, wants[1])
+    sec = ctx.time_e2e([px[0].array, px[1].array], [out[0].array, out[1].array], 20, async_download=False)
+    assert np.array_equal(out[0].array, wants[0]) and np.array_equal(out[1].array, wants[1])
+    ctx.close()
+
+
+
+def test_overlapping_small_launches(gpu, port):
+    """Small matrices use a handful of CTAs, so several consecutive launches are resident at the same time
+    (a launch neither waits for its predecessor before working nor holds back its successor): the
+    accumulator rotation, its reuse guard, the x flags and the end-of-launch drains must still give exact
+    results, launch after launch."""
+    for rows_, nnz_, rpp in ((600, 9000, 0), (3000, 40000, 1024), (20000, 300000, 0)):
+        rows, cols, indptr, indices, data = matgen.rmat_csr(rows_, nnz_, 31)
+        r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
+        words = port.quantize(data)
+        rng = np.random.default_rng(9)
+        xs = [port.quantize(rng.random(c2, dtype=np.float32)) for _ in range(2)]
+        wants = [port.spmv_q824(ip2, indices, words, x) for x in xs]
+        ctx = capi.Context(0, capi.IMPL_FIXED)
+        ctx.upload_matrix_csr(r2, c2, ip2, indices, words, rpp)
+        px = [capi.PinnedArray(c2) for _ in range(2)]
+        py = [capi.PinnedArray(r2) for _ in range(2)]
+        for k in range(2):
+            px[k].array[:] = xs[k]
+        xh, yh = [b.array for b in px], [b.array for b in py]
+        for rep in range(3):
+            ctx.time_e2e(xh, yh, 300, async_download=True)
+            assert np.array_equal(yh[0], wants[0]) and np.array_equal(yh[1], wants[1]), (rows_, rep)
+        # many launches on one vector, then the other, results only at the end
+        for k in (0, 1, 0, 1):
+            ctx.upload_vector(xh[k])
+            for _ in range(37):
+                ctx.spmv()
+            assert np.array_equal(ctx.download_result(), wants[k]), (rows_, k)
+        if rpp:
+            nparts = (r2 + rpp - 1) // rpp
+            for it in range(20):
+                k = it & 1
+                ctx.upload_vector(xh[k])
+                for j in range(nparts):
+                    ctx.spmv_row_partition(j, min(rpp, r2 - j * rpp) // 16, 1, nparts, c2)
+                ctx.download_result_async(yh[k])
+            ctx.sync()
+            assert np.array_equal(yh[0], wants[0]) and np.array_equal(yh[1], wants[1])
+        # float arithmetic through the same machinery
+        ctx.close()
+    rows, cols, indptr, indices, data = matgen.rmat_csr(3000, 40000, 33)
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
+    x = np.zeros(c2, np.float32)
+    x[:cols] = np.random.default_rng(2).random(cols, dtype=np.float32)
+    ctx = capi.Context(0, capi.IMPL_FLOAT_POB)
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, data)
+    ctx.upload_vector(x)
+    for _ in range(50):
+        ctx.spmv()
+    check_float(ctx.download_result(), port, ip2, indices, data, x)
+    ctx.close()
+
+
 @pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p) for p in FIXTURES])
 @pytest.mark.parametrize("impl", hsoracle.IMPLS)
 def test_reference_fixture_through_cpsr_images(gpu, port, path, impl):
