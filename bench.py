@@ -57,15 +57,24 @@ WORKLOADS = {
 WORKLOAD = "c2"
 
 
-def workload(rank):
-    """Synthetic shard for `rank` (rank 0 == the single-GPU workload). Default: the C2 stand-in."""
-    from hisparse_b200 import matgen
-    rows, cols, indptr, indices, data = WORKLOADS[WORKLOAD][2](matgen, rank)
+SHARD_ONE_MATRIX = False
+
+
+def workload(rank, world=1):
+    """Synthetic input of `rank`. Default (weak scaling): every rank gets its own matrix of the workload's
+    size (rank 0 == the single-GPU workload). --shard-one-matrix (strong scaling, BASELINE config C4):
+    ONE matrix, cut into nnz-balanced row blocks (hisparse_b200/sharding.py), rank g keeps block g."""
+    from hisparse_b200 import matgen, sharding
+    rows, cols, indptr, indices, data = WORKLOADS[WORKLOAD][2](matgen, 0 if SHARD_ONE_MATRIX else rank)
     if WORKLOADS[WORKLOAD][1] == "fixed":
         data = (data * np.float32(0.05)).astype(np.float32)  # keeps most row sums below saturation
     r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)  # util_round_csr_matrix_dim
     x = np.zeros(c2, np.float32)
     x[:cols] = np.random.default_rng(SEED).random(cols, dtype=np.float32)
+    if SHARD_ONE_MATRIX and world > 1:
+        bounds = sharding.shard_bounds(ip2, world)
+        ip2, indices, data = sharding.extract_shard(ip2, indices, data, bounds[rank], bounds[rank + 1])
+        r2 = bounds[rank + 1] - bounds[rank]
     return r2, c2, ip2, indices, data, x
 
 
@@ -214,9 +223,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
                     help="c2 (default) is the bench line; the others are extra measurements")
+    ap.add_argument("--shard-one-matrix", action="store_true",
+                    help="N > 1: row-block shards of ONE matrix (strong scaling) instead of one matrix per rank")
     args = ap.parse_args()
-    global WORKLOAD
+    global WORKLOAD, SHARD_ONE_MATRIX
     WORKLOAD = args.workload
+    SHARD_ONE_MATRIX = args.shard_one_matrix
     if args.impl == "reference":
         return run_reference(args)
 
@@ -231,7 +243,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    r2, c2, ip2, indices, data, x = workload(rank)
+    r2, c2, ip2, indices, data, x = workload(rank, world)
     nnz = int(ip2[-1])
     from hisparse_b200 import matgen
     impl = WORKLOADS[WORKLOAD][1]
@@ -308,6 +320,16 @@ def main():
     ctx.spmv()
     y2 = ctx.download_result()
     want = (y, y2)
+    sum_abs = None
+    if impl != "fixed":                 # sum_i |a_i x_i| per row, the scale of fp32 rounding noise (plain numpy)
+        starts = np.minimum(ip2[:-1].astype(np.int64), max(nnz - 1, 0))
+        empty = np.diff(ip2.astype(np.int64)) == 0
+        sum_abs = []
+        for xv in (xw, xw2):
+            t = np.abs(data.astype(np.float64)) * np.abs(xv.view(np.float32).astype(np.float64)[indices])
+            sa = np.add.reduceat(t, starts) if nnz else np.zeros(r2)
+            sa[empty] = 0.0
+            sum_abs.append(sa)
 
     def same(got, k):
         # fixed point: sums of non-negative integers are order independent -> identical words; float: the
@@ -316,7 +338,7 @@ def main():
             ok = np.array_equal(got, want[k])
         else:
             a, b = got.view(np.float32).astype(np.float64), want[k].view(np.float32).astype(np.float64)
-            ok = bool(np.all(np.abs(a - b) <= 1e-4 * np.maximum(np.abs(b), 1e-3)))
+            ok = bool(np.all(np.abs(a - b) <= 2e-5 * sum_abs[k] + 1e-30))   # each run is within 1e-5 * sum|a_i x_i|
         if not ok:
             ctx.close()
             raise SystemExit("bench: end-to-end result %d differs from the device-resident run" % k)
@@ -370,14 +392,17 @@ def main():
             "metric": "SpMV GOPS (2*nnz/t, sw/benchmark.cpp:312-346)", "value": gops, "unit": "GOPS",
             "gbps": 8.0 * nnz_all / 2 ** 30 / sec_per_spmv,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "ms_per_spmv": 1e3 * sec_per_spmv, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_spmv": 1e3 * sec_per_spmv, "higher_is_better": True,
+            "scaling": "strong" if (SHARD_ONE_MATRIX and world > 1) else "weak", "vs_baseline": None,
             "dtype": "u32 Q8.24 (ap_ufixed<32,8,AP_RND,AP_SAT>), 64-bit accumulate" if impl == "fixed" else "f32",
             "data": "synthetic",
             "config": {"workload": (WORKLOADS[WORKLOAD][0] % ()) + ", nnz=%d per GPU" % nnz,
                        "spmv_per_step": B, "l2_policy": "inputs larger than L2: %d HBM replicas of the matrix "
                        "(%.0f MB each) used round-robin" % (replicas, st["format_bytes"] / 1e6),
-                       "sharding": "row-block shard per GPU, x replicated (one NCCL broadcast before timing), "
-                                   "no data-path collective" if world > 1 else "single GPU",
+                       "sharding": (("nnz-balanced row-block shards of ONE matrix" if SHARD_ONE_MATRIX else
+                                     "one matrix of the workload's size per GPU") +
+                                    ", x replicated (one NCCL broadcast before timing), no data-path collective")
+                       if world > 1 else "single GPU",
                        "tile_cols": st["tile_cols"], "col_tiles": st["n_col_tiles"], "grid": st["grid"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "spmv_tiles_kernel<%s>" % ("FixedArith" if impl == "fixed" else "FloatArith"),

@@ -105,6 +105,11 @@ def lib():
         getattr(L, n).argtypes = [vp]
         getattr(L, n).restype = vp
     L.hsb_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    L.hsb_axpb_to_vector.argtypes = [vp, u32, u32, u32]
+    L.hsb_device_x_next.argtypes = [vp]
+    L.hsb_device_x_next.restype = vp
+    L.hsb_vector_commit.argtypes = [vp]
+    L.hsb_iterate.argtypes = [vp, C.c_int, u32, u32]
     L.hsb_debug_trace.argtypes = [vp, vp, sz]
     L.hsb_debug_timeline.argtypes = [vp, vp, sz]
     L.hsb_debug_plan.argtypes = [vp, vp, vp, sz]
@@ -304,6 +309,19 @@ class Context:
         _check(lib().hsb_time_e2e(self.h, xs, ys, x_host[0].size, y_host[0].size, iters, 1 if async_download else 0,
                                   C.byref(sec)))
         return sec.value
+
+    def axpb_to_vector(self, alpha_word, beta_word, col_offset=0):
+        _check(lib().hsb_axpb_to_vector(self.h, int(alpha_word), int(beta_word), col_offset))
+
+    def device_x_next(self):
+        return lib().hsb_device_x_next(self.h)
+
+    def vector_commit(self):
+        _check(lib().hsb_vector_commit(self.h))
+
+    def iterate(self, iters, alpha_word, beta_word):
+        """iters x { x <- alpha (*) A x (+) beta } on the device (PageRank-style power iteration)"""
+        _check(lib().hsb_iterate(self.h, iters, int(alpha_word), int(beta_word)))
 
     def set_option(self, name, value):
         _check(lib().hsb_set_option(self.h, name.encode(), int(value)))

@@ -110,6 +110,7 @@ struct hsb_ctx {
     // (three buffers in flag-pipeline mode, so that an upload never has to wait for the launch in flight)
     uint32_t *d_x[kXBuffers] = {nullptr, nullptr, nullptr, nullptr};
     int x_latest = 0;                     // buffer the next launch reads
+    int x_next_buf = -1;                  // buffer hsb_axpb_to_vector wrote and hsb_vector_commit will make current
     bool x_dirty = false;                 // uploaded since the last launch: the launch must wait for the copy
     // y is double buffered too: the launch that follows a deferred download drains into d_y[y_cur], the
     // copy engine reads that buffer out, and later launches drain into the other one
@@ -167,7 +168,7 @@ void free_matrix(hsb_ctx *c) {
     cudaFree(c->d_y[0]); cudaFree(c->d_y[1]); cudaFree(c->d_cta_seg); cudaFree(c->d_segs);
     c->d_y[0] = c->d_y[1] = nullptr; c->x_latest = 0; c->x_dirty = false; c->d_cta_seg = nullptr; c->d_segs = nullptr;
     c->y_cur = 0; c->y_busy[0] = c->y_busy[1] = false; c->pending_dl.active = false;
-    c->x_wait_buf = -1;
+    c->x_wait_buf = -1; c->x_next_buf = -1;
     c->drain_pending = false; c->acc_cur = 0;
     c->have_matrix = false;
 }
@@ -475,7 +476,7 @@ hsb_ctx *hsb_create(int device, int impl) {
         delete c;
         return nullptr;
     }
-    c->sm_count = prop.multiProcessorCount;
+    c->sm_count = prop.multiProcessorCount * hsb::kCtasPerSm;    // CTA slots the launch plans are cut for
     e = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_h2d_b, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
@@ -865,6 +866,74 @@ int hsb_time_e2e(hsb_ctx *c, const void *const x_host[2], void *const y_host[2],
     }
     if ((rc = hsb_sync(c))) return rc;
     *seconds_per_spmv = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / iters;
+    return HSB_OK;
+}
+
+// ---- iterative callers: x <- alpha (*) y (+) beta on the device ------------------------------------------
+int hsb_axpb_to_vector(hsb_ctx *c, uint32_t alpha_word, uint32_t beta_word, uint32_t col_offset) {
+    if (!c) return set_err(HSB_EINVAL, "null context");
+    if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
+    if (col_offset >= c->x_words) return set_err(HSB_EINVAL, "col_offset beyond the vector");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->pending_dl.active) { int rc = finish(c); if (rc) return rc; }
+    // the buffer being written must not be the target of an upload still in flight
+    CUDA_TRY(cudaStreamSynchronize(c->s_h2d));
+    CUDA_TRY(cudaStreamSynchronize(c->s_h2d_b));
+    const int nb = c->flags_mode ? kXBuffers : 2;
+    const int b = (c->x_latest + 1) % nb;
+    const int yb = c->y_cur;
+    if (c->y_busy[yb]) {                                   // a download still reads y: order the rewrite behind it
+        if (c->flags_mode)
+            MEMOP_TRY(g_wait32((CUstream)c->stream, (CUdeviceptr)(c->d_flags + kFlagYFree + yb), c->y_dl_seq[yb], CU_STREAM_WAIT_VALUE_GEQ));
+        else
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_ydone, 0));
+        c->y_busy[yb] = false;
+    }
+    void *acc = nullptr;
+    if (c->drain_pending && c->drain_begin == 0 && c->drain_end == c->rows) {
+        acc = c->d_acc[(c->acc_cur + kAccBuffers - 1) % kAccBuffers];       // fused: drain + update in one pass
+        c->drain_pending = false;
+    } else {
+        int rc = finish(c);
+        if (rc) return rc;
+    }
+    // an ordinary (non-programmatic) launch: it starts when every SpMV before it has completed, and the next
+    // SpMV -- which reads the vector written here -- starts when it has completed
+    CUDA_TRY(hsb::launch_axpb(c->arith, acc, c->d_y[yb], c->d_x[b], c->rows, c->x_words, alpha_word, beta_word, col_offset,
+                              c->rows, c->stream));
+    c->launches++;
+    c->x_next_buf = b;
+    return HSB_OK;
+}
+
+void *hsb_device_x_next(hsb_ctx *c) {
+    if (!c || !c->have_matrix) return nullptr;
+    const int nb = c->flags_mode ? kXBuffers : 2;
+    return c->d_x[c->x_next_buf >= 0 ? c->x_next_buf : (c->x_latest + 1) % nb];
+}
+
+int hsb_vector_commit(hsb_ctx *c) {
+    if (!c) return set_err(HSB_EINVAL, "null context");
+    if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
+    const int nb = c->flags_mode ? kXBuffers : 2;
+    c->x_latest = c->x_next_buf >= 0 ? c->x_next_buf : (c->x_latest + 1) % nb;
+    c->x_next_buf = -1;
+    c->x_wait_buf = -1;                                    // written on the compute stream: plain stream order
+    c->x_dirty = false;
+    if (!c->flags_mode) CUDA_TRY(cudaEventRecord(c->ev_xfree[c->x_latest ^ 1], c->stream));
+    return HSB_OK;
+}
+
+int hsb_iterate(hsb_ctx *c, int iters, uint32_t alpha_word, uint32_t beta_word) {
+    if (!c || iters < 0) return set_err(HSB_EINVAL, "bad argument");
+    if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
+    if (c->rows > c->x_words) return set_err(HSB_EINVAL, "hsb_iterate needs rows <= columns (x <- f(A x))");
+    for (int k = 0; k < iters; k++) {
+        int rc = hsb_spmv(c);
+        if (rc == HSB_OK) rc = hsb_axpb_to_vector(c, alpha_word, beta_word, 0);
+        if (rc == HSB_OK) rc = hsb_vector_commit(c);
+        if (rc) return rc;
+    }
     return HSB_OK;
 }
 

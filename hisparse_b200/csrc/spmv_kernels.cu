@@ -92,6 +92,12 @@ struct FixedArith {                                   // ap_ufixed<32,8,AP_RND,A
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
         return v;
     }
+    // alpha (*) y (+) beta with the PE's product rounding / saturation (pe.h:64) and saturating add (pe.h:72)
+    static __device__ __forceinline__ uint32_t axpb(uint32_t alpha, uint32_t y, uint32_t beta) {
+        unsigned long long q = ((unsigned long long)alpha * y + 0x800000ull) >> 24;
+        q = min(q, 0xFFFFFFFFull) + beta;
+        return q > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)q;
+    }
     static __device__ __forceinline__ uint32_t drain(void *acc, uint32_t row) {
         unsigned long long *p = reinterpret_cast<unsigned long long *>(acc) + row;
         unsigned long long a = __ldcg(p);
@@ -114,6 +120,9 @@ struct FloatArith {                                   // fp32 multiply, then fp3
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
         return v;
+    }
+    static __device__ __forceinline__ uint32_t axpb(uint32_t alpha, uint32_t y, uint32_t beta) {
+        return __float_as_uint(__fadd_rn(__fmul_rn(__uint_as_float(alpha), __uint_as_float(y)), __uint_as_float(beta)));
     }
     static __device__ __forceinline__ uint32_t drain(void *acc, uint32_t row) {
         float *p = reinterpret_cast<float *>(acc) + row;
@@ -258,7 +267,7 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, uint64_t *bar,
 }
 
 template <class A>
-__global__ void __launch_bounds__(kThreads, 1) spmv_tiles_kernel(const SpmvParams p) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const SpmvParams p) {
     unsigned char *smem_raw = reinterpret_cast<unsigned char *>(xs);
     __shared__ __align__(8) uint64_t bar;
 
@@ -357,7 +366,31 @@ __global__ void drain_kernel(void *acc, uint32_t *y, uint32_t row_begin, uint32_
     if (blockIdx.x == 0 && threadIdx.x == 0) (void)A::drain(acc, trash_row);
 }
 
+// The step between two SpMVs of an iterative caller (PageRank-style x <- alpha (*) A x (+) beta): final y
+// from the row accumulators (or from y itself when they are already drained), and the next vector written
+// straight into an x buffer at this GPU's row offset -- no host round trip, no separate drain.
+template <class A>
+__global__ void axpb_kernel(void *acc, uint32_t *y, uint32_t *x_next, uint32_t rows, uint32_t x_limit, uint32_t alpha,
+                            uint32_t beta, uint32_t col_offset, uint32_t trash_row) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+        uint32_t v;
+        if (acc) { v = A::drain(acc, r); y[r] = v; } else { v = y[r]; }
+        if (col_offset + r < x_limit) x_next[col_offset + r] = A::axpb(alpha, v, beta);
+    }
+    if (acc && blockIdx.x == 0 && threadIdx.x == 0) (void)A::drain(acc, trash_row);
+}
+
 }  // namespace
+
+cudaError_t launch_axpb(int arith, void *acc, uint32_t *y, uint32_t *x_next, uint32_t rows, uint32_t x_limit,
+                        uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, cudaStream_t stream) {
+    const int grid = (int)std::min<uint32_t>((std::max(rows, 1u) + 255) / 256, 148u * 8u);
+    if (arith == kArithFixed)
+        axpb_kernel<FixedArith><<<grid, 256, 0, stream>>>(acc, y, x_next, rows, x_limit, alpha, beta, col_offset, trash_row);
+    else
+        axpb_kernel<FloatArith><<<grid, 256, 0, stream>>>(acc, y, x_next, rows, x_limit, alpha, beta, col_offset, trash_row);
+    return cudaGetLastError();
+}
 
 cudaError_t configure_kernels() {
     cudaError_t e = cudaFuncSetAttribute(spmv_tiles_kernel<FixedArith>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -94,6 +94,9 @@ cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, uint32_t smem_
 // drain only: y[r] = clamp(acc[r]), acc[r] = 0 for r in [row_begin, row_end) and the trash slot
 cudaError_t launch_drain(int arith, void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end,
                          uint32_t trash_row, cudaStream_t stream);
+// y = final result of the last launch (drained from acc when acc != null); x_next[col_offset + r] = alpha (*) y[r] (+) beta
+cudaError_t launch_axpb(int arith, void *acc, uint32_t *y, uint32_t *x_next, uint32_t rows, uint32_t x_limit,
+                        uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, cudaStream_t stream);
 cudaError_t configure_kernels();
 
 }  // namespace hsb

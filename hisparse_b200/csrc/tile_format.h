@@ -37,6 +37,10 @@ constexpr int kLanes = 32;
 #ifndef HSB_WARPS_PER_CTA
 #define HSB_WARPS_PER_CTA 32
 #endif
+#ifndef HSB_CTAS_PER_SM
+#define HSB_CTAS_PER_SM 1
+#endif
+constexpr int kCtasPerSm = HSB_CTAS_PER_SM;               // resident CTAs per SM the grid is sized for (tuning builds)
 constexpr int kWarpsPerCta = HSB_WARPS_PER_CTA;           // warps of the kernel's one CTA per SM (the planner cuts shares for them)
 constexpr int kSlotBlock = 4;                            // non-zeros per lane per load step
 constexpr int kStepElems = kLanes * kSlotBlock;          // 128 elements per slice step

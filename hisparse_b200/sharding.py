@@ -30,3 +30,22 @@ def extract_shard(indptr, indices, data, r0, r1):
 
 def gather_counts(bounds):
     return [bounds[g + 1] - bounds[g] for g in range(len(bounds) - 1)]
+
+
+def allgather_blocks(dist, x_full, bounds):
+    """In-place all-gather of unequal contiguous blocks: rank g owns x_full[bounds[g]:bounds[g+1]] (a torch
+    tensor on the rank's device, or on the CPU with gloo) and receives everybody else's block. NCCL has no
+    all-gather-v; with a handful of ranks one broadcast per block is the simplest exact equivalent and
+    moves the same bytes over NVLink. Used by iterative callers: x(k+1) = f(y(k)) where every rank
+    produced the y block of its row shard (hsb_axpb_to_vector writes it at its row offset)."""
+    for g in range(len(bounds) - 1):
+        if bounds[g + 1] > bounds[g]:
+            dist.broadcast(x_full[bounds[g]:bounds[g + 1]], src=g)
+
+
+def axpb_q824(alpha_word, y_words, beta_word):
+    """alpha (*) y (+) beta in ap_ufixed<32,8,AP_RND,AP_SAT> on raw words: rounded saturating product
+    (spmv/libfpga/pe.h:64) and saturating add (pe.h:72) -- what hsb_axpb_to_vector computes (fixed)."""
+    q = (np.uint64(alpha_word) * y_words.astype(np.uint64) + np.uint64(1 << 23)) >> np.uint64(24)
+    q = np.minimum(q, np.uint64(0xFFFFFFFF)) + np.uint64(beta_word)
+    return np.minimum(q, np.uint64(0xFFFFFFFF)).astype(np.uint32)

@@ -140,6 +140,21 @@ int hsb_top_wrapper(int impl, const void *const matrix_hbm[HSB_NUM_HBM_CHANNELS]
                     unsigned part_len, unsigned num_col_partitions, unsigned num_partitions,
                     unsigned num_cols);
 
+/* ---- iterative callers (the step either side of SpMV in the reference's intended use: PageRank-style
+ * x <- alpha (*) A x (+) beta, unit_tests/test_app.cpp:51-136) -- everything stays on the device ---------
+ * alpha / beta are 32-bit value words (Q8.24 or fp32 bits); the arithmetic is the implementation's own:
+ * fixed = rounded saturating product (spmv/libfpga/pe.h:64) + saturating add (pe.h:72); float = fp32
+ * multiply then add (spmv-fp/libfpga/pe-pob.h:64-66). */
+/* Finalise y of the last SpMV and write x_next[col_offset + r] = alpha (*) y[r] (+) beta for every row r into
+ * the NEXT vector buffer (fused with the row drain). col_offset = this GPU's first row when the matrix is
+ * row-block sharded: each rank fills its slice, then the ranks all-gather hsb_device_x_next() in place. */
+int hsb_axpb_to_vector(hsb_ctx *ctx, uint32_t alpha_word, uint32_t beta_word, uint32_t col_offset);
+void *hsb_device_x_next(hsb_ctx *ctx);
+/* the next vector buffer becomes the one the following SpMVs read (after the all-gather, if any) */
+int hsb_vector_commit(hsb_ctx *ctx);
+/* single GPU, rows <= cols: iters x { hsb_spmv; hsb_axpb_to_vector(alpha, beta, 0); hsb_vector_commit } */
+int hsb_iterate(hsb_ctx *ctx, int iters, uint32_t alpha_word, uint32_t beta_word);
+
 /* ---- measurement and multi-GPU plumbing (no reference counterpart) ------------------------ */
 int hsb_get_stats(hsb_ctx *ctx, hsb_stats *out);
 /* keep n copies of the matrix in HBM and rotate through them on successive hsb_spmv() calls so

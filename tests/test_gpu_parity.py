@@ -492,3 +492,113 @@ def test_cpsr_images_large_float_stall(gpu, port):
     ctx.spmv_row_partition(0, r2 // 16, m.n_col_parts, m.n_col_parts * m.n_row_parts, c2)
     check_float(ctx.download_result(), port, ip2, indices, data, x)
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------
+# iterative callers: x <- alpha (*) A x (+) beta on the device
+# ------------------------------------------------------------------------------------------
+def _pagerank_matrix(n, nnz, seed):
+    """column-stochastic-ish link matrix: value = 1 / out-degree of the source column"""
+    rows, cols, indptr, indices, _ = matgen.rmat_csr(n, nnz, seed)
+    outdeg = np.maximum(np.bincount(indices, minlength=cols), 1)
+    data = (1.0 / outdeg[indices]).astype(np.float32)
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 128)
+    return r2, c2, ip2, indices, data
+
+
+def test_iterate_fixed_bit_exact(gpu, port):
+    from hisparse_b200 import sharding
+    r2, c2, ip2, indices, data = _pagerank_matrix(6000, 90000, 41)
+    assert r2 == c2
+    words = port.quantize(data)
+    alpha, beta = int(port.quantize(np.float32([0.85]))[0]), int(port.quantize(np.float32([0.15 / 8]))[0])
+    x0 = port.quantize(np.full(c2, 1.0 / 8, np.float32))
+    x = x0.copy()
+    for _ in range(7):
+        x = sharding.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, x), beta)
+    want = port.spmv_q824(ip2, indices, words, x)
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+    ctx.upload_vector(x0)
+    ctx.iterate(7, alpha, beta)
+    ctx.spmv()
+    assert np.array_equal(ctx.download_result(), want)
+    # step by step, with downloads in between and an upload restarting the iteration
+    ctx.upload_vector(x0)
+    x = x0.copy()
+    for k in range(3):
+        ctx.spmv()
+        y = ctx.download_result()
+        assert np.array_equal(y, port.spmv_q824(ip2, indices, words, x)), k
+        ctx.axpb_to_vector(alpha, beta, 0)
+        ctx.vector_commit()
+        x = sharding.axpb_q824(alpha, y, beta)
+    ctx.spmv()
+    assert np.array_equal(ctx.download_result(), port.spmv_q824(ip2, indices, words, x))
+    ctx.close()
+
+
+def test_iterate_float(gpu, port):
+    r2, c2, ip2, indices, data = _pagerank_matrix(6000, 90000, 43)
+    alpha, beta = np.float32(0.85), np.float32(0.15 / r2)
+    x = np.full(c2, 1.0 / r2, np.float64)
+    x0 = x.astype(np.float32)
+    for _ in range(6):
+        y64, _ = port.spmv_f64(ip2, indices, data, x.astype(np.float32))
+        x = float(alpha) * y64 + float(beta)
+    y64, sa = port.spmv_f64(ip2, indices, data, x.astype(np.float32))
+    ctx = capi.Context(0, capi.IMPL_FLOAT_POB)
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, data)
+    ctx.upload_vector(x0)
+    ctx.iterate(6, int(alpha.view(np.uint32)), int(beta.view(np.uint32)))
+    ctx.spmv()
+    y = ctx.download_result().view(np.float32).astype(np.float64)
+    ctx.close()
+    # rounding differences compound over the iterations: 1e-4 of the row's absolute sum after 7 SpMVs
+    assert np.all(np.abs(y - y64) <= 1e-4 * sa + 1e-12)
+
+
+def test_iterate_two_row_block_shards(gpu, port):
+    """The multi-GPU iteration on one device: two contexts hold the two row-block shards, each writes its
+    slice of the next vector at its row offset (hsb_axpb_to_vector), the slices are exchanged (the
+    all-gather of tools/pagerank.py) and committed. Bit-equal to the single-context iteration."""
+    import torch
+    from hisparse_b200 import sharding
+    r2, c2, ip2, indices, data = _pagerank_matrix(5000, 70000, 45)
+    words = port.quantize(data)
+    alpha, beta = int(port.quantize(np.float32([0.85]))[0]), int(port.quantize(np.float32([0.02]))[0])
+    x0 = port.quantize(np.full(c2, 0.125, np.float32))
+    x = x0.copy()
+    for _ in range(4):
+        x = sharding.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, x), beta)
+    want = port.spmv_q824(ip2, indices, words, x)
+    bounds = sharding.shard_bounds(ip2, 2)
+    ctxs = []
+    for g in range(2):
+        sip, six, sw = sharding.extract_shard(ip2, indices, words, bounds[g], bounds[g + 1])
+        c = capi.Context(0, capi.IMPL_FIXED)
+        c.upload_matrix_csr(bounds[g + 1] - bounds[g], c2, sip, six, sw)
+        c.upload_vector(x0)
+        ctxs.append(c)
+
+    class Dev:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+    for _ in range(4):
+        for g, c in enumerate(ctxs):
+            c.spmv()
+            c.axpb_to_vector(alpha, beta, bounds[g])
+            c.sync()
+        nxt = [torch.as_tensor(Dev(c.device_x_next(), c2), device="cuda:0") for c in ctxs]
+        nxt[0][bounds[1]:bounds[2]] = nxt[1][bounds[1]:bounds[2]]
+        nxt[1][bounds[0]:bounds[1]] = nxt[0][bounds[0]:bounds[1]]
+        torch.cuda.synchronize()
+        for c in ctxs:
+            c.vector_commit()
+    got = []
+    for c in ctxs:
+        c.spmv()
+        got.append(c.download_result())
+        c.close()
+    assert np.array_equal(np.concatenate(got), want)

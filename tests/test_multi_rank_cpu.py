@@ -72,3 +72,44 @@ def test_shard_bounds_balance():
         nnz = [int(ip2[b[g + 1]]) - int(ip2[b[g]]) for g in range(world)]
         assert max(nnz) <= 1.25 * (sum(nnz) / world) + 128 * 500
         assert all(x % 128 == 0 for x in b[:-1])
+
+
+def _pagerank_worker(rank, world, port_no, out_dir):
+    """x <- alpha (*) A x (+) beta over row-block shards: every rank multiplies its shard, writes its slice
+    of the next vector at its row offset and the slices are all-gathered in place -- the loop of
+    tools/pagerank.py with the oracle standing in for the GPU engine."""
+    sys.path.insert(0, ROOT)
+    from hisparse_b200 import matgen, sharding
+    from oracle import hsoracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    port = hsoracle.Port()
+    rows, cols, indptr, indices, data = matgen.rmat_csr(4000, 60000, 91)
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 128)
+    words = port.quantize((data * np.float32(0.05)).astype(np.float32))
+    alpha, beta = int(port.quantize(np.float32([0.85]))[0]), int(port.quantize(np.float32([0.01]))[0])
+    bounds = sharding.shard_bounds(ip2, world)
+    sip, six, sw = sharding.extract_shard(ip2, indices, words, bounds[rank], bounds[rank + 1])
+    x = port.quantize(np.full(c2, 0.25, np.float32))
+    for _ in range(5):
+        y_block = port.spmv_q824(sip, six, sw, x)                         # hsb_spmv on this rank's shard
+        nxt = torch.zeros(c2, dtype=torch.int64)
+        nxt[bounds[rank]:bounds[rank + 1]] = torch.from_numpy(            # hsb_axpb_to_vector(alpha, beta, bounds[rank])
+            sharding.axpb_q824(alpha, y_block, beta).astype(np.int64))
+        sharding.allgather_blocks(dist, nxt, bounds)
+        x = nxt.numpy().astype(np.uint32)                                 # hsb_vector_commit
+    if rank == 0:
+        ref = port.quantize(np.full(c2, 0.25, np.float32))
+        for _ in range(5):
+            ref = sharding.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, ref), beta)
+        np.save(os.path.join(out_dir, "pr.npy"), np.array([int(np.array_equal(x, ref))]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_iteration(tmp_path):
+    world = 2
+    port_no = 31500 + os.getpid() % 2000
+    mp.spawn(_pagerank_worker, args=(world, port_no, str(tmp_path)), nprocs=world, join=True)
+    assert np.load(tmp_path / "pr.npy")[0] == 1
