@@ -19,6 +19,7 @@ HEADER = os.path.join(ROOT, "include", "hisparse_b200.h")
 IMPL_FIXED, IMPL_FLOAT_POB, IMPL_FLOAT_STALL = 0, 1, 2
 IMPL_BY_NAME = {"fixed": 0, "float_pob": 1, "float_stall": 2}
 NUM_HBM_CHANNELS, PACK_SIZE = 16, 8
+PEER_BLOB_BYTES = 160
 
 
 class HsbError(RuntimeError):
@@ -110,6 +111,9 @@ def lib():
     L.hsb_device_x_next.restype = vp
     L.hsb_vector_commit.argtypes = [vp]
     L.hsb_iterate.argtypes = [vp, C.c_int, u32, u32]
+    L.hsb_peer_export.argtypes = [vp, vp]
+    L.hsb_peer_connect.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.hsb_axpb_to_peers.argtypes = [vp, u32, u32, u32]
     L.hsb_debug_trace.argtypes = [vp, vp, sz]
     L.hsb_debug_timeline.argtypes = [vp, vp, sz]
     L.hsb_debug_plan.argtypes = [vp, vp, vp, sz]
@@ -318,6 +322,19 @@ class Context:
 
     def vector_commit(self):
         _check(lib().hsb_vector_commit(self.h))
+
+    def peer_export(self):
+        blob = np.zeros(PEER_BLOB_BYTES, np.uint8)
+        _check(lib().hsb_peer_export(self.h, _ptr(blob)))
+        return blob
+
+    def peer_connect(self, world, rank, blobs):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8)
+        assert blobs.size == world * PEER_BLOB_BYTES
+        _check(lib().hsb_peer_connect(self.h, world, rank, _ptr(blobs)))
+
+    def axpb_to_peers(self, alpha_word, beta_word, col_offset):
+        _check(lib().hsb_axpb_to_peers(self.h, int(alpha_word), int(beta_word), col_offset))
 
     def iterate(self, iters, alpha_word, beta_word):
         """iters x { x <- alpha (*) A x (+) beta } on the device (PageRank-style power iteration)"""

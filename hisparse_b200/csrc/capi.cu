@@ -108,9 +108,17 @@ struct hsb_ctx {
     // x is double buffered so that the upload of the next vector (copy stream) overlaps the SpMV that
     // still reads the current one; x_words words each (padded to whole tiles, zero filled)
     // (three buffers in flag-pipeline mode, so that an upload never has to wait for the launch in flight)
-    uint32_t *d_x[kXBuffers] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t *d_x[kXBuffers] = {nullptr, nullptr, nullptr, nullptr};   // slices of ONE allocation (d_x[0]): one IPC handle
+    // multi-GPU iteration over peer memory (hsb_peer_connect): next-x buffers and arrival flags of every rank
+    uint32_t *d_peer = nullptr;           // [0..15] arrival flags written by the ranks, [32] completion ticket
+    int peer_world = 0, peer_rank = 0;
+    uint32_t *peer_x[hsb::kMaxPeers] = {};     // rank g's d_x[0] (this process's own pointer for g == rank)
+    uint32_t *peer_flags[hsb::kMaxPeers] = {}; // rank g's d_peer
+    size_t x_stride = 0;                  // words between consecutive x buffers
+    uint32_t peer_seq = 0;
     int x_latest = 0;                     // buffer the next launch reads
     int x_next_buf = -1;                  // buffer hsb_axpb_to_vector wrote and hsb_vector_commit will make current
+    bool x_next_from_peers = false;       // ... filled by all ranks (hsb_axpb_to_peers): the next SpMV polls their arrival flags
     bool x_dirty = false;                 // uploaded since the last launch: the launch must wait for the copy
     // y is double buffered too: the launch that follows a deferred download drains into d_y[y_cur], the
     // copy engine reads that buffer out, and later launches drain into the other one
@@ -163,7 +171,11 @@ namespace {
 void free_matrix(hsb_ctx *c) {
     for (auto &m : c->mats) m.release();
     c->mats.clear();
-    for (int b = 0; b < kXBuffers; b++) { cudaFree(c->d_x[b]); c->d_x[b] = nullptr; c->x_reader_seq[b] = 0; }
+    for (int g = 0; g < c->peer_world; g++)
+        if (g != c->peer_rank) { if (c->peer_x[g]) cudaIpcCloseMemHandle(c->peer_x[g]); if (c->peer_flags[g]) cudaIpcCloseMemHandle(c->peer_flags[g]); }
+    c->peer_world = 0;
+    cudaFree(c->d_x[0]); cudaFree(c->d_peer); c->d_peer = nullptr;
+    for (int b = 0; b < kXBuffers; b++) { c->d_x[b] = nullptr; c->x_reader_seq[b] = 0; }
     for (int b = 0; b < kAccBuffers; b++) { cudaFree(c->d_acc[b]); c->d_acc[b] = nullptr; }
     cudaFree(c->d_y[0]); cudaFree(c->d_y[1]); cudaFree(c->d_cta_seg); cudaFree(c->d_segs);
     c->d_y[0] = c->d_y[1] = nullptr; c->x_latest = 0; c->x_dirty = false; c->d_cta_seg = nullptr; c->d_segs = nullptr;
@@ -239,11 +251,15 @@ int install_matrix(hsb_ctx *c, const hsb::TiledMatrix &M, const DeviceMatrix &d,
     CUDA_TRY(cudaMemcpyAsync(c->d_segs, segs.data(), segs.size() * sizeof(hsb::Segment), cudaMemcpyHostToDevice, c->stream));
     // x is padded to whole tiles so that every bulk copy of a tile stays inside the buffer
     c->x_words = M.n_col_tiles * M.tile_cols;
+    c->x_stride = ((size_t)c->x_words + 8 + 31) & ~(size_t)31;
+    CUDA_TRY(cudaMalloc(&c->d_x[0], c->x_stride * kXBuffers * 4));
+    CUDA_TRY(cudaMemsetAsync(c->d_x[0], 0, c->x_stride * kXBuffers * 4, c->stream));
     for (int b = 0; b < kXBuffers; b++) {
-        CUDA_TRY(cudaMalloc(&c->d_x[b], (size_t)c->x_words * 4 + 16));
-        CUDA_TRY(cudaMemsetAsync(c->d_x[b], 0, (size_t)c->x_words * 4, c->stream));
+        c->d_x[b] = c->d_x[0] + b * c->x_stride;
         if (b < 2) CUDA_TRY(cudaEventRecord(c->ev_xfree[b], c->stream));
     }
+    CUDA_TRY(cudaMalloc(&c->d_peer, 64 * 4));
+    CUDA_TRY(cudaMemsetAsync(c->d_peer, 0, 64 * 4, c->stream));
     for (int b = 0; b < 2; b++) {
         CUDA_TRY(cudaMalloc(&c->d_y[b], (size_t)std::max(c->rows, 1u) * 4));
         CUDA_TRY(cudaMemsetAsync(c->d_y[b], 0, (size_t)std::max(c->rows, 1u) * 4, c->stream));
@@ -328,7 +344,8 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
         if (c->x_wait_buf >= 0 && c->xwait_once && c->x_wait_launch && (int32_t)(*c->h_done - c->x_wait_launch) >= 0)
             c->x_wait_buf = -1;
         if (c->x_wait_buf >= 0) {
-            p.wait_x_flag = c->d_flags + kFlagXReady + c->x_wait_buf; p.wait_x_val = c->x_wait_val;
+            p.wait_x_flag = c->d_flags + kFlagXReady + c->x_wait_buf; p.wait_x_val = c->x_wait_val; p.wait_x_count = 1;
+            if (c->x_wait_buf >= kXBuffers) { p.wait_x_flag = c->d_peer; p.wait_x_count = (uint32_t)c->peer_world; }   // slices from all ranks
             if (!c->x_wait_launch) c->x_wait_launch = c->launch_seq + 1;
         }
         if (c->drain_pending && c->y_busy[yb]) {
@@ -919,8 +936,96 @@ int hsb_vector_commit(hsb_ctx *c) {
     c->x_latest = c->x_next_buf >= 0 ? c->x_next_buf : (c->x_latest + 1) % nb;
     c->x_next_buf = -1;
     c->x_wait_buf = -1;                                    // written on the compute stream: plain stream order
+    if (c->x_next_from_peers) {                            // ... except the other ranks' slices: arrival flags
+        c->x_wait_buf = kXBuffers; c->x_wait_val = c->peer_seq; c->x_wait_launch = 0;
+        c->x_next_from_peers = false;
+    }
     c->x_dirty = false;
     if (!c->flags_mode) CUDA_TRY(cudaEventRecord(c->ev_xfree[c->x_latest ^ 1], c->stream));
+    return HSB_OK;
+}
+
+// ---- the same across GPUs, over peer memory (one process per GPU, CUDA IPC) ------------------------------
+namespace {
+struct PeerBlob {                      // what hsb_peer_export hands to the other ranks (HSB_PEER_BLOB_BYTES)
+    cudaIpcMemHandle_t x, flags;
+    uint64_t x_stride;
+    uint32_t x_words, x_latest;
+};
+static_assert(sizeof(PeerBlob) <= HSB_PEER_BLOB_BYTES, "blob size");
+}  // namespace
+
+int hsb_peer_export(hsb_ctx *c, void *blob) {
+    if (!c || !blob) return set_err(HSB_EINVAL, "null argument");
+    if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    { int rc = quiesce(c); if (rc) return rc; }
+    PeerBlob b;
+    std::memset(&b, 0, sizeof b);
+    CUDA_TRY(cudaIpcGetMemHandle(&b.x, c->d_x[0]));
+    CUDA_TRY(cudaIpcGetMemHandle(&b.flags, c->d_peer));
+    b.x_stride = c->x_stride; b.x_words = c->x_words; b.x_latest = (uint32_t)c->x_latest;
+    std::memset(blob, 0, HSB_PEER_BLOB_BYTES);
+    std::memcpy(blob, &b, sizeof b);
+    return HSB_OK;
+}
+
+int hsb_peer_connect(hsb_ctx *c, int world, int rank, const void *blobs) {
+    if (!c || !blobs || world < 1 || world > hsb::kMaxPeers || rank < 0 || rank >= world)
+        return set_err(HSB_EINVAL, "bad argument");
+    if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
+    if (!c->flags_mode) return set_err(HSB_ESTATE, "the peer iteration needs the flag pipeline (stream memory operations)");
+    CUDA_TRY(cudaSetDevice(c->device));
+    { int rc = quiesce(c); if (rc) return rc; }
+    for (int g = 0; g < world; g++) {
+        PeerBlob b;
+        std::memcpy(&b, (const char *)blobs + (size_t)g * HSB_PEER_BLOB_BYTES, sizeof b);
+        if (b.x_words != c->x_words || b.x_stride != c->x_stride || (int)b.x_latest != c->x_latest)
+            return set_err(HSB_EINVAL, "rank " + std::to_string(g) + " has a different vector layout or upload history");
+        if (g == rank) { c->peer_x[g] = c->d_x[0]; c->peer_flags[g] = c->d_peer; continue; }
+        void *px = nullptr, *pf = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&px, b.x, cudaIpcMemLazyEnablePeerAccess));
+        CUDA_TRY(cudaIpcOpenMemHandle(&pf, b.flags, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_x[g] = (uint32_t *)px; c->peer_flags[g] = (uint32_t *)pf;
+    }
+    c->peer_world = world; c->peer_rank = rank; c->peer_seq = 0;
+    return HSB_OK;
+}
+
+int hsb_axpb_to_peers(hsb_ctx *c, uint32_t alpha_word, uint32_t beta_word, uint32_t col_offset) {
+    if (!c) return set_err(HSB_EINVAL, "null context");
+    if (!c->have_matrix || c->peer_world < 1) return set_err(HSB_ESTATE, "call hsb_peer_connect first");
+    if (col_offset >= c->x_words) return set_err(HSB_EINVAL, "col_offset beyond the vector");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->pending_dl.active) { int rc = finish(c); if (rc) return rc; }
+    const int b = (c->x_latest + 1) % kXBuffers;
+    const int yb = c->y_cur;
+    if (c->y_busy[yb]) {
+        MEMOP_TRY(g_wait32((CUstream)c->stream, (CUdeviceptr)(c->d_flags + kFlagYFree + yb), c->y_dl_seq[yb], CU_STREAM_WAIT_VALUE_GEQ));
+        c->y_busy[yb] = false;
+    }
+    void *acc = nullptr;
+    if (c->drain_pending && c->drain_begin == 0 && c->drain_end == c->rows) {
+        acc = c->d_acc[(c->acc_cur + kAccBuffers - 1) % kAccBuffers];
+        c->drain_pending = false;
+    } else {
+        int rc = finish(c);
+        if (rc) return rc;
+    }
+    hsb::PeerTargets t;
+    std::memset(&t, 0, sizeof t);
+    t.world = c->peer_world;
+    for (int g = 0; g < c->peer_world; g++) {
+        t.x_next[g] = c->peer_x[g] + (size_t)b * c->x_stride;
+        t.flag[g] = c->peer_flags[g] + c->peer_rank;
+    }
+    // Every rank runs the same sequence, so buffer b is the same buffer everywhere; a rank can be at most one
+    // iteration ahead of the slowest one (its next SpMV waits for everybody's slice), and four buffers rotate.
+    CUDA_TRY(hsb::launch_axpb_peers(c->arith, acc, c->d_y[yb], t, c->rows, c->x_words, alpha_word, beta_word, col_offset,
+                                    c->rows, ++c->peer_seq, c->d_peer + 32, c->stream));
+    c->launches++;
+    c->x_next_buf = b;
+    c->x_next_from_peers = true;
     return HSB_OK;
 }
 

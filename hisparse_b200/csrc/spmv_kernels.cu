@@ -49,14 +49,14 @@ __device__ __forceinline__ uint2 ldg_stream64(const uint2 *p) {
     return r;
 }
 // Bounded spin on a sequence flag another engine writes (a stream memory operation on a copy stream):
-// true once (int)(flag - val) >= 0. About a quarter of a second worth of polls, then give up rather than hang the GPU.
+// true once (int)(flag - val) >= 0. About a second worth of polls, then give up rather than hang the GPU.
 __device__ __forceinline__ unsigned long long globaltimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 __device__ __forceinline__ bool wait_flag_geq(const uint32_t *flag, uint32_t val) {
-    for (uint32_t i = 0; i < (1u << 18); i++) {
+    for (uint32_t i = 0; i < (1u << 20); i++) {
         uint32_t v;
         // relaxed: what is read afterwards (x through the TMA / async proxy, which does not go through L1) was
         // written to device memory by the copy engine before the flag; an acquire here costs ~3 us per launch
@@ -311,7 +311,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
             const uint32_t cnt = __ldg(&sg->cnt_ge[lane]);
             // stage the x tile: the vector loader + vecbuf writer of the reference
             if (tid == 0) {
-                if (g == g0 && p.wait_x_flag && !wait_flag_geq(p.wait_x_flag, p.wait_x_val)) atomicExch(p.error_flag, 1u);
+                if (g == g0 && p.wait_x_flag)
+                    for (uint32_t i = 0; i < p.wait_x_count; i++)
+                        if (!wait_flag_geq(p.wait_x_flag + i, p.wait_x_val)) atomicExch(p.error_flag, 1u);
                 if (tl && blockIdx.x == 0 && g == g0) tl[1] = globaltimer();
                 fence_proxy_async();
                 const uint32_t bytes = h1.x * 4u;
@@ -380,7 +382,44 @@ __global__ void axpb_kernel(void *acc, uint32_t *y, uint32_t *x_next, uint32_t r
     if (acc && blockIdx.x == 0 && threadIdx.x == 0) (void)A::drain(acc, trash_row);
 }
 
+template <class A>
+__global__ void axpb_peers_kernel(void *acc, uint32_t *y, const PeerTargets t, uint32_t rows, uint32_t x_limit,
+                                  uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, uint32_t seq,
+                                  uint32_t *ticket) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+        uint32_t v;
+        if (acc) { v = A::drain(acc, r); y[r] = v; } else { v = y[r]; }
+        if (col_offset + r < x_limit) {
+            const uint32_t w = A::axpb(alpha, v, beta);
+            for (int g = 0; g < t.world; g++) t.x_next[g][col_offset + r] = w;      // NVLink peer stores, coalesced
+        }
+    }
+    if (acc && blockIdx.x == 0 && threadIdx.x == 0) (void)A::drain(acc, trash_row);
+    // grid-wide completion: the last CTA publishes the slice's arrival on every rank
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+            *ticket = 0u;
+            __threadfence_system();
+            for (int g = 0; g < t.world; g++)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.flag[g]), "r"(seq) : "memory");
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_axpb_peers(int arith, void *acc, uint32_t *y, const PeerTargets &t, uint32_t rows, uint32_t x_limit,
+                              uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, uint32_t seq,
+                              uint32_t *ticket, cudaStream_t stream) {
+    const int grid = (int)std::min<uint32_t>((std::max(rows, 1u) + 255) / 256, 148u * 4u);
+    if (arith == kArithFixed)
+        axpb_peers_kernel<FixedArith><<<grid, 256, 0, stream>>>(acc, y, t, rows, x_limit, alpha, beta, col_offset, trash_row, seq, ticket);
+    else
+        axpb_peers_kernel<FloatArith><<<grid, 256, 0, stream>>>(acc, y, t, rows, x_limit, alpha, beta, col_offset, trash_row, seq, ticket);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_axpb(int arith, void *acc, uint32_t *y, uint32_t *x_next, uint32_t rows, uint32_t x_limit,
                         uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, cudaStream_t stream) {

@@ -71,8 +71,9 @@ struct SpmvParams {
     // Flag pipeline (host <-> device overlap without stream events between launches, which would undo the
     // programmatic-dependent-launch overlap of consecutive SpMVs). All flags are 32-bit sequence
     // numbers in device memory, compared cyclically; null pointers switch the feature off.
-    const uint32_t *wait_x_flag;  // the copy stream writes wait_x_val here once this launch's x has landed
-    uint32_t wait_x_val;
+    const uint32_t *wait_x_flag;  // the copy stream writes wait_x_val here once this launch's x has landed; in a multi-GPU
+    uint32_t wait_x_val;          // iteration: wait_x_count consecutive flags, one per rank whose slice of x must have arrived
+    uint32_t wait_x_count;
     const uint32_t *wait_y_flag;  // ... and wait_y_val here once the last download of `y` has been read out
     uint32_t wait_y_val;
     uint32_t *done_dev;           // launch `seq` publishes seq - 1 here (device memory) once its predecessor has completed ...
@@ -97,6 +98,18 @@ cudaError_t launch_drain(int arith, void *acc, uint32_t *y, uint32_t row_begin, 
 // y = final result of the last launch (drained from acc when acc != null); x_next[col_offset + r] = alpha (*) y[r] (+) beta
 cudaError_t launch_axpb(int arith, void *acc, uint32_t *y, uint32_t *x_next, uint32_t rows, uint32_t x_limit,
                         uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, cudaStream_t stream);
+// Multi-GPU form of launch_axpb: the slice alpha (*) y (+) beta is stored into the next x buffer of EVERY rank
+// (peer pointers over NVLink, this rank included) at col_offset, and when the whole grid has finished, `seq`
+// is written into this rank's slot of every rank's arrival-flag array -- compute and all-gather in one kernel.
+constexpr int kMaxPeers = 16;
+struct PeerTargets {
+    uint32_t *x_next[kMaxPeers];   // next x buffer of rank g
+    uint32_t *flag[kMaxPeers];     // &arrival[my rank] in rank g's flag array
+    int world;
+};
+cudaError_t launch_axpb_peers(int arith, void *acc, uint32_t *y, const PeerTargets &t, uint32_t rows, uint32_t x_limit,
+                              uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, uint32_t seq,
+                              uint32_t *ticket, cudaStream_t stream);
 cudaError_t configure_kernels();
 
 }  // namespace hsb

@@ -152,6 +152,17 @@ int hsb_axpb_to_vector(hsb_ctx *ctx, uint32_t alpha_word, uint32_t beta_word, ui
 void *hsb_device_x_next(hsb_ctx *ctx);
 /* the next vector buffer becomes the one the following SpMVs read (after the all-gather, if any) */
 int hsb_vector_commit(hsb_ctx *ctx);
+/* Multi-GPU iteration without the host: one process per GPU; after every rank has uploaded its row-block
+ * shard and the same x, the ranks exchange hsb_peer_export blobs (e.g. torch.distributed.all_gather) and
+ * call hsb_peer_connect (CUDA IPC, peer access over NVLink). hsb_axpb_to_peers then stores this rank's
+ * slice of the next vector into the next x buffer of EVERY rank and raises an arrival flag there when the
+ * kernel has finished -- the compute step and the all-gather are one kernel -- and after
+ * hsb_vector_commit the next hsb_spmv polls the arrival flags of all ranks before it stages x. No NCCL
+ * call, no host synchronisation inside the iteration. */
+#define HSB_PEER_BLOB_BYTES 160
+int hsb_peer_export(hsb_ctx *ctx, void *blob);
+int hsb_peer_connect(hsb_ctx *ctx, int world, int rank, const void *blobs /* world x HSB_PEER_BLOB_BYTES */);
+int hsb_axpb_to_peers(hsb_ctx *ctx, uint32_t alpha_word, uint32_t beta_word, uint32_t col_offset);
 /* single GPU, rows <= cols: iters x { hsb_spmv; hsb_axpb_to_vector(alpha, beta, 0); hsb_vector_commit } */
 int hsb_iterate(hsb_ctx *ctx, int iters, uint32_t alpha_word, uint32_t beta_word);
 

@@ -602,3 +602,27 @@ def test_iterate_two_row_block_shards(gpu, port):
         got.append(c.download_result())
         c.close()
     assert np.array_equal(np.concatenate(got), want)
+
+
+def test_peer_iteration_single_rank(gpu, port):
+    """hsb_peer_export / hsb_peer_connect / hsb_axpb_to_peers with a world of one (the multi-GPU runs are
+    tools/pagerank.py --p2p --check under torchrun): same kernel, same arrival-flag wait, bit-exact."""
+    from hisparse_b200 import sharding
+    r2, c2, ip2, indices, data = _pagerank_matrix(6000, 90000, 47)
+    words = port.quantize(data)
+    alpha, beta = int(port.quantize(np.float32([0.85]))[0]), int(port.quantize(np.float32([0.02]))[0])
+    x0 = port.quantize(np.full(c2, 0.125, np.float32))
+    x = x0.copy()
+    for _ in range(9):
+        x = sharding.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, x), beta)
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+    ctx.upload_vector(x0)
+    ctx.peer_connect(1, 0, ctx.peer_export())
+    for _ in range(9):
+        ctx.spmv()
+        ctx.axpb_to_peers(alpha, beta, 0)
+        ctx.vector_commit()
+    ctx.spmv()
+    assert np.array_equal(ctx.download_result(), port.spmv_q824(ip2, indices, words, x))
+    ctx.close()

@@ -33,6 +33,9 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--impl", default="float_pob", choices=["fixed", "float_pob", "float_stall"])
     ap.add_argument("--check", action="store_true", help="compare with a host iteration (oracle; small sizes)")
+    ap.add_argument("--p2p", action="store_true",
+                    help="N > 1: exchange the x blocks inside the update kernel over peer memory (hsb_axpb_to_peers) "
+                         "instead of NCCL broadcasts issued by the host")
     args = ap.parse_args()
     from hisparse_b200 import capi, matgen, sharding
     rank = int(os.environ.get("RANK", "0"))
@@ -61,8 +64,23 @@ def main():
     ctx.upload_matrix_csr(bounds[rank + 1] - bounds[rank], c2, sip, six, sw)
     ctx.upload_vector(x0)
     ctx.sync()
+    p2p = args.p2p and dist is not None
+    if p2p:
+        mine = torch.from_numpy(ctx.peer_export()).cuda(local)
+        blobs = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(blobs, mine)
+        ctx.peer_connect(world, rank, torch.cat(blobs).cpu().numpy())
+        dist.barrier()
 
     def iterate(n):
+        if p2p:
+            # compute + all-gather in one kernel, arrival flags polled by the next SpMV: the host only enqueues
+            for _ in range(n):
+                ctx.spmv()
+                ctx.axpb_to_peers(alpha, beta, bounds[rank])
+                ctx.vector_commit()
+            ctx.sync()
+            return
         for _ in range(n):
             ctx.spmv()
             ctx.axpb_to_vector(alpha, beta, bounds[rank])
@@ -86,21 +104,30 @@ def main():
     y = ctx.download_result()
     out = {"nodes": r2, "nnz": int(ip2[-1]), "impl": args.impl, "n_gpus": world, "iters": args.iters,
            "ms_per_iteration": 1e3 * sec, "gops": 2.0 * int(ip2[-1]) / sec / 1e9,
-           "what": "spmv + fused drain/axpb + in-place NCCL all-gather of x blocks + commit, per iteration"}
-    if args.check and rank == 0 and world == 1:
+           "exchange": "peer-memory stores + arrival flags inside the update kernel" if p2p else
+                       ("NCCL broadcasts issued by the host" if world > 1 else "none (single GPU)"),
+           "what": "spmv + fused drain/axpb + exchange of the x blocks + commit, per iteration"}
+    if args.check:
         from oracle import hsoracle
         port = hsoracle.Port()
         if fixed:
             x = x0.copy()
             for _ in range(args.iters + 3):
                 x = sharding.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, x), beta)
-            out["parity"] = "bit-exact" if np.array_equal(y, port.spmv_q824(ip2, indices, words, x)) else "MISMATCH"
+            want = port.spmv_q824(ip2, indices, words, x)[bounds[rank]:bounds[rank + 1]]
+            ok = np.array_equal(y, want)
+            if dist is not None:
+                t = torch.tensor([int(ok)], device="cuda:%d" % local)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                ok = bool(t.item())
+            out["parity"] = "bit-exact on every rank" if ok else "MISMATCH"
         else:
             x = x0f.astype(np.float64)
             for _ in range(args.iters + 3):
                 y64, _ = port.spmv_f64(ip2, indices, data, x.astype(np.float32))
                 x = 0.85 * y64 + 0.15
             y64, sa = port.spmv_f64(ip2, indices, data, x.astype(np.float32))
+            y64, sa = y64[bounds[rank]:bounds[rank + 1]], sa[bounds[rank]:bounds[rank + 1]]
             err = float(np.max(np.abs(y.view(np.float32) - y64) / (sa + 1e-30)))
             out["parity"] = "max |err| / sum|a x| = %.2e" % err
     if rank == 0:
