@@ -20,9 +20,12 @@
 //                                                         routing by row, no read-after-write hazard
 //   pe dump + result_packer + axis_merge + result_drain one red.global.add per lane stream (or per warp when
 //     (pe.h:95-116, spmv_cluster.h:133-193,                a slice holds one row) into the row accumulator;
-//      stream_utils.h:36-75, spmv_result_drain.cpp)        the accumulators are double buffered and drained
-//                                                         (clamp, store y, re-zero) in the prologue of the
-//                                                         next launch or by a drain kernel at sync time
+//      stream_utils.h:36-75, spmv_result_drain.cpp)        four accumulator buffers rotate and launch n drains
+//                                                         the buffer of launch n-1 (clamp, store y, re-zero) at
+//                                                         its very end, or a drain kernel does at sync time
+//
+// Consecutive launches overlap freely (griddepcontrol.launch_dependents first, griddepcontrol.wait last):
+// see the comments in spmv_tiles_kernel.
 //
 // Arithmetic:
 //   fixed  : VAL_T = ap_ufixed<32,8,AP_RND,AP_SAT> (spmv/libfpga/common.h:38). product =
