@@ -319,8 +319,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
                 const uint32_t bytes = h1.x * 4u;
                 mbar_arrive_expect_tx(&bar, bytes);
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(p.x + h0.w);
-                for (uint32_t off = 0; off < bytes; off += kBulkPiece)
+                // Many CTAs stage the same tile at the same moment. Each starts at a different piece and wraps
+                // around, so that at any instant they pull from different L2 slices instead of queueing on one.
+                const uint32_t pieces = (bytes + kBulkPiece - 1) / kBulkPiece;
+                uint32_t k = blockIdx.x % pieces;
+                for (uint32_t i = 0; i < pieces; i++) {
+                    const uint32_t off = k * kBulkPiece;
                     bulk_g2s(smem_raw + kXTileOffset + off, src + off, min(kBulkPiece, bytes - off), &bar);
+                    k = k + 1 == pieces ? 0 : k + 1;
+                }
             }
             // this warp's equal-cost share of the segment (host plan)
             const uint32_t ta = __ldg(&sg->warp_t[warp]), tb = __ldg(&sg->warp_t[warp + 1]);

@@ -47,7 +47,10 @@ constexpr int kThreads = kWarps * 32;
 constexpr uint32_t kXTileBytes = kMaxTileCols * 4;   // 224 KB
 constexpr uint32_t kXTileOffset = kColBias * 4;      // xs[0..7] = 0: what padding slots (column id 0) gather
 constexpr uint32_t kSmemBytes = kXTileBytes + kXTileOffset;   // upper bound; a launch asks for what its tiles need
-constexpr uint32_t kBulkPiece = 16384;               // bytes per cp.async.bulk
+#ifndef HSB_BULK_PIECE
+#define HSB_BULK_PIECE 16384
+#endif
+constexpr uint32_t kBulkPiece = HSB_BULK_PIECE;      // bytes per cp.async.bulk
 #ifndef HSB_PREFETCH
 #define HSB_PREFETCH 4
 #endif
