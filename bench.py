@@ -51,6 +51,12 @@ WORKLOADS = {
            lambda m, r: m.rmat_csr(N_NODES, NNZ_TARGET, SEED + r)),
     "c3": ("C3: transformer-sized 512x33288 Bernoulli mask 50 %%, fp32 (float_pob)", "float_pob",
            lambda m, r: m.bernoulli_csr(512, 33288, 0.5, 0xC0FFEE03 + r)),
+    "t95": ("transformer-sized 512x33288 Bernoulli mask 5 %%, fp32 (float_pob)", "float_pob",
+            lambda m, r: m.bernoulli_csr(512, 33288, 0.05, 0xC0FFEE03 + r)),
+    # C5: one row-block shard per GPU of the 100 M x 100 M power-law matrix (12.5 M rows, ~245 M non-zeros each: the
+    # whole matrix at 8 GPUs), generated AND formatted on the device (hsb_synth_powerlaw_csr_device)
+    "c5s": ("C5 shard: rows [rank*12.5M, +12.5M) of the 100M x 100M power-law matrix (alpha 2.1, mean degree 20, "
+            "80 %% of the columns within +-2^20 of the diagonal), generated on the device, fp32", "float_pob", None),
     "c4": ("C4: ogbl-ppa-sized symmetric R-MAT 576289^2, fp32", "float_pob",
            lambda m, r: m.rmat_csr(576289, 42_460_000, 0xC0FFEE04 + r, symmetric=True, oversample=1.5)),
 }
@@ -158,6 +164,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if WORKLOAD == "c5s":
+        raise SystemExit("bench: the C5 shard is generated on the GPU; the reference arm runs the host-generated workloads")
     r2, c2, ip2, indices, data, x = workload(0)
     nnz = int(ip2[-1])
     kind, one = _reference_timers(r2, c2, ip2, indices, data, x)
@@ -243,17 +251,27 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    r2, c2, ip2, indices, data, x = workload(rank, world)
-    nnz = int(ip2[-1])
     from hisparse_b200 import matgen
     impl = WORKLOADS[WORKLOAD][1]
-    if impl == "fixed":
-        words, xw = matgen.quantize_q824(data), matgen.quantize_q824(x)  # host-side float -> VAL_T conversion
-    else:
-        words, xw = data.view(np.uint32), x.view(np.uint32)
-
     ctx = capi.Context(local, impl)
-    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+    if WORKLOAD == "c5s":
+        # the shard never exists on the host in CSR form before the run; it is downloaded afterwards for the checks
+        r2, c2 = 12_500_000, 100_000_000
+        dcsr = capi.DeviceCsr.powerlaw(local, r2, c2, first_global_row=rank * r2, seed=0xC0FFEE05)
+        ctx.upload_matrix_csr_device(dcsr)
+        ip2, indices, words = dcsr.download()
+        dcsr.free()
+        data = words.view(np.float32)
+        x = np.random.default_rng(SEED).random(c2, dtype=np.float32)
+        xw = x.view(np.uint32)
+    else:
+        r2, c2, ip2, indices, data, x = workload(rank, world)
+        if impl == "fixed":
+            words, xw = matgen.quantize_q824(data), matgen.quantize_q824(x)  # host-side float -> VAL_T conversion
+        else:
+            words, xw = data.view(np.uint32), x.view(np.uint32)
+        ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+    nnz = int(ip2[-1])
     st = ctx.stats()
     replicas = max(2, int(np.ceil(2.5 * L2_BYTES / max(st["format_bytes"], 1))))
     ctx.set_replicas(replicas)
@@ -270,7 +288,7 @@ def main():
     ctx.spmv()
     y = ctx.download_result()            # checked bit-for-bit against the oracle in the cpu_baseline leg (N=1)
 
-    B = args.batch
+    B = args.batch if WORKLOAD != "c5s" else max(1, min(args.batch, 16))       # a C5-shard SpMV takes milliseconds
     launches0 = ctx.stats()["kernel_launches"]
     sampler = ClockSampler(local)
     if rank == 0:
@@ -297,7 +315,7 @@ def main():
     kernel_ms = total_ms / (launches2 - launches1)
     # the same kernel launched in isolation (an event pair around every launch defeats the
     # programmatic-dependent-launch overlap between consecutive launches)
-    _, kernel_ms_isolated = ctx.time_spmv(0, min(args.steps * B, 512), kernel=True)
+    _, kernel_ms_isolated = ctx.time_spmv(0, min(args.steps * B, 512 if WORKLOAD != "c5s" else 8), kernel=True)
     if dist is not None:
         import torch
         t = torch.tensor([total_ms, float(nnz)], dtype=torch.float64, device="cuda:%d" % local)
@@ -348,12 +366,12 @@ def main():
     px[0].array[:] = xw
     px[1].array[:] = xw2
     xh, yh = [b_.array for b_ in px], [b_.array for b_ in py]
-    n_e2e = max(64, min(args.steps * B, 4096))
+    n_e2e = max(64, min(args.steps * B, 4096)) if WORKLOAD != "c5s" else 16
     n_e2e += n_e2e & 1
     ctx.time_e2e(xh, yh, 16, async_download=False)
     barrier()
     # (a) strictly synchronous, (b) pipelined; both issued from C by hsb_time_e2e through the public entry points
-    n_sync = max(64, n_e2e // 4)
+    n_sync = max(64, n_e2e // 4) if WORKLOAD != "c5s" else 8
     e2e_sync_s = ctx.time_e2e(xh, yh, n_sync + (n_sync & 1), async_download=False)
     same(yh[0], 0)
     same(yh[1], 1)
@@ -366,10 +384,11 @@ def main():
     # the same pipelined sequence issued call by call from Python (ctypes): what the pytest glue sees
     barrier()
     t0 = time.perf_counter()
-    for k in range(256):
+    n_py = 256 if WORKLOAD != "c5s" else 8
+    for k in range(n_py):
         ctx.upload_vector(xh[k & 1]); ctx.spmv(); ctx.download_result_async(yh[k & 1])
     ctx.sync()
-    e2e_py_s = (time.perf_counter() - t0) / 256
+    e2e_py_s = (time.perf_counter() - t0) / n_py
     same(yh[0], 0)
     same(yh[1], 1)
     if dist is not None:

@@ -158,6 +158,7 @@ struct hsb_ctx {
     // checks that launch n + 1 -- the one that re-zeroed it -- is complete.
     void *d_acc[kAccBuffers] = {nullptr, nullptr, nullptr, nullptr};
     int acc_cur = 0;
+    int acc_bufs = kAccBuffers;           // buffers in rotation: 4, or 2 with a wait at launch start (accumulators >> L2)
     bool drain_pending = false;           // d_acc[acc_cur ^ 1] holds sums that are not in y yet
     uint32_t drain_begin = 0, drain_end = 0;
     unsigned long long *d_trace = nullptr; // optional per-warp clock stamps of the last launch
@@ -265,7 +266,13 @@ int install_matrix(hsb_ctx *c, const hsb::TiledMatrix &M, const DeviceMatrix &d,
         CUDA_TRY(cudaMemsetAsync(c->d_y[b], 0, (size_t)std::max(c->rows, 1u) * 4, c->stream));
     }
     const size_t esz = c->arith == hsb::kArithFixed ? 8 : 4;
-    for (int b = 0; b < kAccBuffers; b++) {
+    // Four buffers let consecutive launches overlap without any wait, but every launch then updates rows in a
+    // buffer that was last touched three launches ago. When the buffers together no longer fit in L2 (C5
+    // shards: 12.5 M rows) the row updates would all miss; such launches are long anyway, so they rotate two
+    // buffers and wait for their predecessor before the first row update instead.
+    c->acc_bufs = ((size_t)c->rows + 1) * esz * kAccBuffers > (size_t)96 << 20 ? 2 : kAccBuffers;
+    if (const char *e = std::getenv("HSB_ACC_BUFFERS")) c->acc_bufs = std::atoi(e) == 2 ? 2 : kAccBuffers;
+    for (int b = 0; b < c->acc_bufs; b++) {
         CUDA_TRY(cudaMalloc(&c->d_acc[b], ((size_t)c->rows + 1) * esz));
         CUDA_TRY(cudaMemsetAsync(c->d_acc[b], 0, ((size_t)c->rows + 1) * esz, c->stream));
     }
@@ -368,7 +375,8 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
     p.seq = ++c->launch_seq;
     p.done_dev = c->d_flags + kFlagDoneDev;
     p.error_flag = c->d_flags + kFlagError;
-    if (p.seq > 3) { p.guard_flag = p.done_dev; p.guard_val = p.seq - 3; }
+    if (c->acc_bufs == 2) p.sync_start = 1;
+    else if (p.seq > 3) { p.guard_flag = p.done_dev; p.guard_val = p.seq - 3; }
     p.x = c->d_x[c->x_latest]; p.y = c->d_y[yb];
     if (c->pending_dl.active && c->pending_dl.dev && c->drain_pending) {
         // page-locked destination: the prologue drain writes the result words to the host buffer as well
@@ -376,7 +384,7 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
         p.y_host = c->pending_dl.dev; p.y_host_rows = c->pending_dl.n;
     }
     p.acc = c->d_acc[c->acc_cur];
-    p.drain_acc = c->drain_pending ? c->d_acc[(c->acc_cur + kAccBuffers - 1) % kAccBuffers] : nullptr;
+    p.drain_acc = c->drain_pending ? c->d_acc[(c->acc_cur + c->acc_bufs - 1) % c->acc_bufs] : nullptr;
     p.drain_begin = c->drain_begin; p.drain_end = c->drain_end;
     p.trash_row = c->rows;
     p.trace = c->d_trace;
@@ -402,7 +410,7 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
     c->pending_dl.active = false;                           // (a mapped host buffer was handed to the launch itself)
     c->drain_pending = true;
     c->drain_begin = rb; c->drain_end = re;
-    c->acc_cur = (c->acc_cur + 1) % kAccBuffers;
+    c->acc_cur = (c->acc_cur + 1) % c->acc_bufs;
     return HSB_OK;
 }
 
@@ -419,7 +427,7 @@ int finish(hsb_ctx *c) {
                 CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_ydone, 0));
             c->y_busy[yb] = false;
         }
-        CUDA_TRY(hsb::launch_drain(c->arith, c->d_acc[(c->acc_cur + kAccBuffers - 1) % kAccBuffers], c->d_y[yb], c->drain_begin, c->drain_end, c->rows,
+        CUDA_TRY(hsb::launch_drain(c->arith, c->d_acc[(c->acc_cur + c->acc_bufs - 1) % c->acc_bufs], c->d_y[yb], c->drain_begin, c->drain_end, c->rows,
                                    c->stream));
         c->launches++;
         c->drain_pending = false;
@@ -908,7 +916,7 @@ int hsb_axpb_to_vector(hsb_ctx *c, uint32_t alpha_word, uint32_t beta_word, uint
     }
     void *acc = nullptr;
     if (c->drain_pending && c->drain_begin == 0 && c->drain_end == c->rows) {
-        acc = c->d_acc[(c->acc_cur + kAccBuffers - 1) % kAccBuffers];       // fused: drain + update in one pass
+        acc = c->d_acc[(c->acc_cur + c->acc_bufs - 1) % c->acc_bufs];       // fused: drain + update in one pass
         c->drain_pending = false;
     } else {
         int rc = finish(c);
@@ -1006,7 +1014,7 @@ int hsb_axpb_to_peers(hsb_ctx *c, uint32_t alpha_word, uint32_t beta_word, uint3
     }
     void *acc = nullptr;
     if (c->drain_pending && c->drain_begin == 0 && c->drain_end == c->rows) {
-        acc = c->d_acc[(c->acc_cur + kAccBuffers - 1) % kAccBuffers];
+        acc = c->d_acc[(c->acc_cur + c->acc_bufs - 1) % c->acc_bufs];
         c->drain_pending = false;
     } else {
         int rc = finish(c);

@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
     // the end of launch seq-3. In the steady state that launch is long gone; the guard only ever spins when
     // several small launches are resident at once.
     auto guard = [&]() {
+        if (p.sync_start) asm volatile("griddepcontrol.wait;" ::: "memory");
         if (p.guard_flag) {
             if (lane == 0 && !wait_flag_geq(p.guard_flag, p.guard_val)) atomicExch(p.error_flag, 1u);
             __syncwarp();

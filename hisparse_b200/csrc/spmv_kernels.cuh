@@ -85,6 +85,8 @@ struct SpmvParams {
     uint32_t *done_dev;           // launch `seq` publishes seq - 1 here (device memory) once its predecessor has completed ...
     uint32_t *done_seq;           // ... and here (mapped host memory, read by the host and the copy streams), or null
     uint32_t seq;
+    uint32_t sync_start;          // 1: wait for the predecessor before the first row update (two accumulator buffers in
+                                  // rotation instead of four: long launches with accumulators too big for L2)
     const uint32_t *guard_flag;   // == done_dev when this launch must see guard_val there before its first row update
     uint32_t guard_val;           // (launch seq - 3 has re-zeroed the accumulator buffer), else null
     uint32_t *error_flag;         // set to 1 if a flag wait timed out (the launch then proceeds: no hang)

@@ -16,20 +16,27 @@ def summarize(ctx, n):
     last, t = ctx.timeline()
     seqs = [s for s in range(last - n + 8, last - 2)]
     rows = np.array([t[s & 255] for s in seqs]).astype(np.float64)
-    start, flag, prev, drain, xst, end = [rows[:, i] for i in range(6)]
+    start, flag, prev, drain, xst, end, work = [rows[:, i] for i in range(7)]
     med = lambda a: float(np.median(a)) / 1e3
     return {"period_us": med(np.diff(end)), "duration_us": med(end - start),
             "start_to_flag_us": med(flag - start), "start_to_prev_done_us": med(prev - start),
             "prev_done_to_drain_us": med(drain - prev), "start_to_x_staged_us": med(xst - start),
-            "prev_end_to_start_us": med(start[1:] - end[:-1]), "x_staged_after_prev_done_us": med(xst - prev)}
+            "prev_end_to_start_us": med(start[1:] - end[:-1]), "x_staged_after_prev_done_us": med(xst - prev),
+            "cta0_start_to_work_done_us": med(work - start), "cta0_work_done_to_prev_done_us": med(prev - work),
+            "cta0_prev_done_to_published_us": med(drain - prev)}
 
 
 def main():
+    wl = os.environ.get("TL_WORKLOAD", "c2")
+    bench.WORKLOAD = wl
     r2, c2, ip2, indices, data, x = bench.workload(0)
-    words, xw = matgen.quantize_q824(data), matgen.quantize_q824(x)
-    ctx = capi.Context(0, "fixed")
+    if bench.WORKLOADS[wl][1] == "fixed":
+        words, xw = matgen.quantize_q824(data), matgen.quantize_q824(x)
+    else:
+        words, xw = data.view(np.uint32), x.view(np.uint32)
+    ctx = capi.Context(0, bench.WORKLOADS[wl][1])
     ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
-    ctx.set_replicas(4)
+    ctx.set_replicas(max(2, int(np.ceil(2.5 * 126 * 2 ** 20 / max(ctx.stats()["format_bytes"], 1)))))
     px = [capi.PinnedArray(c2) for _ in range(2)]
     py = [capi.PinnedArray(r2) for _ in range(2)]
     for b in px:
