@@ -16,6 +16,8 @@ def make(config):
         return matgen.random_csr(4096, 4096, 0.01, 0xC0FFEE01)
     if config == "c3":
         return matgen.bernoulli_csr(512, 33288, 0.5, 0xC0FFEE03)
+    if config == "t95":
+        return matgen.bernoulli_csr(512, 33288, 0.05, 0xC0FFEE03)
     if config == "c4":
         return matgen.rmat_csr(576289, 42_460_000, 0xC0FFEE04, symmetric=True, oversample=1.5)
     return matgen.rmat_csr(107614, 13_670_000, 0xC0FFEE02)

@@ -28,6 +28,7 @@ for b in range(t.shape[0]):
     ww = w[b][w[b] > 0]
     print(b, steps[b], slices[b], "|", int(ww.min()) if ww.size else 0, int(ww.mean()) if ww.size else 0, int(ww.max()) if ww.size else 0, int(arrive[b]))
 np.set_printoptions(linewidth=260)
+print("CTA done (cycles/100) by CTA:", (done / 100).astype(int))
 for b in (0, 20, 36, 50, 100):
     print("CTA", b, "per-warp finish/100:", (w[b] / 100).astype(int))
 print("mean over CTAs per warp index /100:", (w.mean(0) / 100).astype(int))
