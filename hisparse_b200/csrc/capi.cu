@@ -733,12 +733,12 @@ int hsb_sync(hsb_ctx *c) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
     c->y_busy[0] = c->y_busy[1] = false;
-    if (c->flags_mode) {
+    {
         uint32_t err = 0;
         CUDA_TRY(cudaMemcpy(&err, c->d_flags + kFlagError, 4, cudaMemcpyDeviceToHost));
         if (err) {
             CUDA_TRY(cudaMemset(c->d_flags + kFlagError, 0, 4));
-            return set_err(HSB_ECUDA, "a kernel gave up waiting for a vector upload / result download flag");
+            return set_err(HSB_ECUDA, "a kernel gave up waiting for a flag (vector upload, result download, peer slice or accumulator reuse)");
         }
     }
     return HSB_OK;

@@ -42,10 +42,3 @@ def allgather_blocks(dist, x_full, bounds):
         if bounds[g + 1] > bounds[g]:
             dist.broadcast(x_full[bounds[g]:bounds[g + 1]], src=g)
 
-
-def axpb_q824(alpha_word, y_words, beta_word):
-    """alpha (*) y (+) beta in ap_ufixed<32,8,AP_RND,AP_SAT> on raw words: rounded saturating product
-    (spmv/libfpga/pe.h:64) and saturating add (pe.h:72) -- what hsb_axpb_to_vector computes (fixed)."""
-    q = (np.uint64(alpha_word) * y_words.astype(np.uint64) + np.uint64(1 << 23)) >> np.uint64(24)
-    q = np.minimum(q, np.uint64(0xFFFFFFFF)) + np.uint64(beta_word)
-    return np.minimum(q, np.uint64(0xFFFFFFFF)).astype(np.uint32)

@@ -353,3 +353,12 @@ class Ref2:
         r, c = C.c_uint32(rows), C.c_uint32(cols)
         self.L.ref2_round_dims(C.byref(r), C.byref(c), C.c_uint32(rd), C.c_uint32(cd))
         return r.value, c.value
+
+
+def axpb_q824(alpha_word, y_words, beta_word):
+    """alpha (*) y (+) beta in ap_ufixed<32,8,AP_RND,AP_SAT> on raw words: the PE's rounded saturating product
+    (spmv/libfpga/pe.h:64: VAL_T incr = mat * vec) followed by its saturating add (pe.h:72) -- the checker for
+    hsb_axpb_to_vector / hsb_axpb_to_peers / hsb_iterate (fixed point)."""
+    q = (np.uint64(alpha_word) * np.asarray(y_words).astype(np.uint64) + np.uint64(1 << 23)) >> np.uint64(24)
+    q = np.minimum(q, np.uint64(0xFFFFFFFF)) + np.uint64(beta_word)
+    return np.minimum(q, np.uint64(0xFFFFFFFF)).astype(np.uint32)

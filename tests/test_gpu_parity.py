@@ -515,7 +515,7 @@ def test_iterate_fixed_bit_exact(gpu, port):
     x0 = port.quantize(np.full(c2, 1.0 / 8, np.float32))
     x = x0.copy()
     for _ in range(7):
-        x = sharding.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, x), beta)
+        x = hsoracle.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, x), beta)
     want = port.spmv_q824(ip2, indices, words, x)
     ctx = capi.Context(0, capi.IMPL_FIXED)
     ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
@@ -532,7 +532,7 @@ def test_iterate_fixed_bit_exact(gpu, port):
         assert np.array_equal(y, port.spmv_q824(ip2, indices, words, x)), k
         ctx.axpb_to_vector(alpha, beta, 0)
         ctx.vector_commit()
-        x = sharding.axpb_q824(alpha, y, beta)
+        x = hsoracle.axpb_q824(alpha, y, beta)
     ctx.spmv()
     assert np.array_equal(ctx.download_result(), port.spmv_q824(ip2, indices, words, x))
     ctx.close()
@@ -570,7 +570,7 @@ def test_iterate_two_row_block_shards(gpu, port):
     x0 = port.quantize(np.full(c2, 0.125, np.float32))
     x = x0.copy()
     for _ in range(4):
-        x = sharding.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, x), beta)
+        x = hsoracle.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, x), beta)
     want = port.spmv_q824(ip2, indices, words, x)
     bounds = sharding.shard_bounds(ip2, 2)
     ctxs = []
@@ -614,7 +614,7 @@ def test_peer_iteration_single_rank(gpu, port):
     x0 = port.quantize(np.full(c2, 0.125, np.float32))
     x = x0.copy()
     for _ in range(9):
-        x = sharding.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, x), beta)
+        x = hsoracle.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, x), beta)
     ctx = capi.Context(0, capi.IMPL_FIXED)
     ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
     ctx.upload_vector(x0)

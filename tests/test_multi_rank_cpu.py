@@ -96,13 +96,13 @@ def _pagerank_worker(rank, world, port_no, out_dir):
         y_block = port.spmv_q824(sip, six, sw, x)                         # hsb_spmv on this rank's shard
         nxt = torch.zeros(c2, dtype=torch.int64)
         nxt[bounds[rank]:bounds[rank + 1]] = torch.from_numpy(            # hsb_axpb_to_vector(alpha, beta, bounds[rank])
-            sharding.axpb_q824(alpha, y_block, beta).astype(np.int64))
+            hsoracle.axpb_q824(alpha, y_block, beta).astype(np.int64))
         sharding.allgather_blocks(dist, nxt, bounds)
         x = nxt.numpy().astype(np.uint32)                                 # hsb_vector_commit
     if rank == 0:
         ref = port.quantize(np.full(c2, 0.25, np.float32))
         for _ in range(5):
-            ref = sharding.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, ref), beta)
+            ref = hsoracle.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, ref), beta)
         np.save(os.path.join(out_dir, "pr.npy"), np.array([int(np.array_equal(x, ref))]))
     dist.barrier()
     dist.destroy_process_group()

@@ -113,7 +113,7 @@ def main():
         if fixed:
             x = x0.copy()
             for _ in range(args.iters + 3):
-                x = sharding.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, x), beta)
+                x = hsoracle.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, x), beta)
             want = port.spmv_q824(ip2, indices, words, x)[bounds[rank]:bounds[rank + 1]]
             ok = np.array_equal(y, want)
             if dist is not None:
