@@ -37,15 +37,42 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// L2 residency: the matrix stream is read exactly once per launch, so it is marked evict-first and leaves
+// the L2 to what IS reused -- the x tiles (read by every CTA of a tile) and above all the row accumulators,
+// which the row updates hit again and again (hypersparse shards: 50-100 MB of accumulators against a 4 GB
+// stream). HSB_L2_HINTS=0 builds without the hints.
+#ifndef HSB_L2_HINTS
+#define HSB_L2_HINTS 1
+#endif
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ uint4 ldg_stream128(const uint4 *p) {
     uint4 r;
+#if HSB_L2_HINTS
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(policy_evict_first()));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#endif
     return r;
 }
 __device__ __forceinline__ uint2 ldg_stream64(const uint2 *p) {
     uint2 r;
+#if HSB_L2_HINTS
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;"
+                 : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(policy_evict_first()));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+#endif
     return r;
 }
 // Bounded spin on a sequence flag another engine writes (a stream memory operation on a copy stream):
@@ -56,6 +83,7 @@ __device__ __forceinline__ unsigned long long globaltimer() {
     return t;
 }
 __device__ __forceinline__ bool wait_flag_geq(const uint32_t *flag, uint32_t val) {
+#pragma unroll 1
     for (uint32_t i = 0; i < (1u << 20); i++) {
         uint32_t v;
         // relaxed: what is read afterwards (x through the TMA / async proxy, which does not go through L1) was
@@ -85,7 +113,13 @@ struct FixedArith {                                   // ap_ufixed<32,8,AP_RND,A
     }
     __device__ __forceinline__ acc_t total() const { return ((acc_t)hi << 8) + lo; }
     static __device__ __forceinline__ void emit(void *acc, uint32_t row, acc_t v) {
-        if (v) atomicAdd(reinterpret_cast<unsigned long long *>(acc) + row, v);    // RED.ADD.64
+        if (!v) return;
+#if HSB_L2_HINTS
+        asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;"
+                     ::"l"(reinterpret_cast<unsigned long long *>(acc) + row), "l"(v), "l"(policy_evict_last()) : "memory");
+#else
+        atomicAdd(reinterpret_cast<unsigned long long *>(acc) + row, v);           // RED.ADD.64
+#endif
     }
     static __device__ __forceinline__ acc_t warp_sum(acc_t v) {
 #pragma unroll
@@ -114,7 +148,12 @@ struct FloatArith {                                   // fp32 multiply, then fp3
     }
     __device__ __forceinline__ acc_t total() const { return s; }
     static __device__ __forceinline__ void emit(void *acc, uint32_t row, acc_t v) {
+#if HSB_L2_HINTS
+        asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;"
+                     ::"l"(reinterpret_cast<float *>(acc) + row), "f"(v), "l"(policy_evict_last()) : "memory");
+#else
         atomicAdd(reinterpret_cast<float *>(acc) + row, v);                        // RED.ADD.F32
+#endif
     }
     static __device__ __forceinline__ acc_t warp_sum(acc_t v) {
 #pragma unroll
