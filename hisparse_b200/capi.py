@@ -123,6 +123,8 @@ def lib():
     L.hsb_format_from_context.restype = vp
     L.hsb_format_stats.argtypes = [vp, C.POINTER(Stats)]
     L.hsb_format_expand.argtypes = [vp, vp, vp, vp]
+    L.hsb_format_plan.argtypes = [vp, u32, vp, sz]
+    L.hsb_format_plan.restype = C.c_longlong
     L.hsb_format_free.argtypes = [vp]
     L.hsb_format_free.restype = None
     L.hsb_cpsr_to_csr.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(sz), C.c_uint, C.c_uint, C.c_uint, C.c_uint,
@@ -418,6 +420,15 @@ class Format:
         s = Stats()
         _check(lib().hsb_format_stats(self.h, C.byref(s)))
         return s.asdict()
+
+    def plan(self, ctas):
+        """-> [n, 4] uint32 records {cta, tile, first step, end step}: the warp shares of the launch plan"""
+        n = lib().hsb_format_plan(self.h, ctas, None, 0)
+        if n < 0:
+            _check(int(n))
+        rec = np.zeros((max(n, 1), 4), np.uint32)
+        lib().hsb_format_plan(self.h, ctas, _ptr(rec), n)
+        return rec[:n]
 
     def expand(self):
         indptr = np.zeros(self.rows + 1, np.uint32)

@@ -35,6 +35,28 @@ int hsb_format_stats(const hsb_format *f, hsb_stats *out) {
     return HSB_OK;
 }
 
+// The launch plan hsb_spmv would use on `ctas` CTAs, flattened for inspection: one record of
+// 4 words per (segment, warp) = {cta, tile, first step, end step} (tile-relative steps).
+long long hsb_format_plan(const hsb_format *f, uint32_t ctas, uint32_t *records, size_t capacity_records) {
+    if (!f || ctas == 0) return HSB_EINVAL;
+    const hsb::TiledMatrix &M = f->M;
+    std::vector<uint32_t> cta_seg;
+    std::vector<hsb::Segment> segs;
+    hsb::plan_launch(M, 0, (uint32_t)M.tiles.size(), ctas, &cta_seg, &segs);
+    size_t n = 0;
+    for (uint32_t b = 0; b < ctas; b++)
+        for (uint32_t g = cta_seg[b]; g < cta_seg[b + 1]; g++)
+            for (int w = 0; w < hsb::kWarpsPerCta; w++) {
+                if (segs[g].warp_t[w] == segs[g].warp_t[w + 1]) continue;
+                if (records && n < capacity_records) {
+                    records[4 * n + 0] = b; records[4 * n + 1] = segs[g].tile;
+                    records[4 * n + 2] = segs[g].warp_t[w]; records[4 * n + 3] = segs[g].warp_t[w + 1];
+                }
+                n++;
+            }
+    return (long long)n;
+}
+
 int hsb_format_expand(const hsb_format *f, uint32_t *indptr, uint32_t *indices, uint32_t *vals) {
     if (!f || !indptr) return HSB_EINVAL;
     const hsb::TiledMatrix &M = f->M;

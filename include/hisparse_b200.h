@@ -241,6 +241,10 @@ int hsb_format_stats(const hsb_format *f, hsb_stats *out);
  * HSB_EINVAL if the stream is internally inconsistent. Entries of a row come back grouped by
  * column tile, CSR order inside a tile. */
 int hsb_format_expand(const hsb_format *f, uint32_t *indptr, uint32_t *indices, uint32_t *vals);
+/* The launch plan the engine would cut for `ctas` CTAs (whole matrix): one record of 4 words per warp share,
+ * {cta, tile, first step, end step} with tile-relative steps. Returns the number of records (call with
+ * records == NULL to size the buffer). Every step of every tile is covered exactly once. */
+long long hsb_format_plan(const hsb_format *f, uint32_t ctas, uint32_t *records, size_t capacity_records);
 void hsb_format_free(hsb_format *f);
 /* Decode reference channel images back to CSR (what hsb_upload_matrix_cpsr does first).
  * indptr: num_rows + 1 words; indices / vals: capacity words each; *nnz receives the count

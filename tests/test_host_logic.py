@@ -116,3 +116,60 @@ def test_quantize_helper_matches_oracle(port):
     v = np.concatenate([rng.random(50000, dtype=np.float32) * 300 - 10,
                         np.array([0, 1, 255.99999, 256, 1e9, -1, 2 ** -25, 3 * 2 ** -25, np.nan, np.inf], np.float32)])
     assert np.array_equal(matgen.quantize_q824(v), port.quantize(v))
+
+
+# ------------------------------------------------------------------------------------------
+# launch planner (host side of hsb_spmv): every step exactly once, balanced, interleaved
+# ------------------------------------------------------------------------------------------
+def _steps_per_tile(fmt, rec):
+    """tile -> sorted list of [first, end) step ranges handed out by the plan"""
+    out = {}
+    for cta, tile, a, b in rec:
+        out.setdefault(int(tile), []).append((int(a), int(b)))
+    return {t: sorted(v) for t, v in out.items()}
+
+
+@pytest.mark.parametrize("name,make,tile_cols,ctas", [
+    ("one_tile", lambda: matgen.rmat_csr(3000, 60000, 5), 0, 148),
+    ("few_tiles", lambda: matgen.random_csr(900, 70000, 0.004, 7), 16384, 148),
+    ("many_tiles", lambda: matgen.random_csr(2000, 400000, 0.0004, 9), 1024, 37),
+    ("tiny", lambda: matgen.random_csr(64, 64, 0.2, 3), 0, 148),
+])
+def test_plan_covers_every_step_once(name, make, tile_cols, ctas):
+    rows, cols, indptr, indices, data = make()
+    fmt = capi.Format(rows, cols, indptr, indices, hsoracle.Port().quantize(data), 0, tile_cols)
+    st = fmt.stats()
+    rec = fmt.plan(ctas)
+    assert rec.shape[0] > 0 and int(rec[:, 0].max()) < ctas
+    total = 0
+    for tile, ranges in _steps_per_tile(fmt, rec).items():
+        # contiguous, non-overlapping, starting at 0
+        pos = 0
+        for a, b in ranges:
+            assert a == pos and b > a, (name, tile, ranges[:4])
+            pos = b
+        total += pos
+    assert total * 128 == st["n_elems"]                    # all stored slots, nothing twice
+    # balance: no CTA gets more than ~1.5x the mean number of steps (+ one slice of slack)
+    per_cta = np.bincount(rec[:, 0], weights=(rec[:, 3] - rec[:, 2]).astype(np.float64), minlength=ctas)
+    busy = per_cta[per_cta > 0]
+    assert busy.max() <= 1.5 * busy.mean() + 40
+
+
+def test_plan_interleaves_tiles_when_there_are_many():
+    """with >= 2 tiles per CTA the k-th tile of CTA b is tile k * ctas + b (up to the drift of the equal-cost
+    cuts, which can hand a CTA the tail of its neighbour's run first): concurrent CTAs work on neighbouring
+    tiles (hypersparse shards)"""
+    rows, cols, indptr, indices, data = matgen.random_csr(1500, 600000, 0.0005, 11)
+    ctas = 20
+    fmt = capi.Format(rows, cols, indptr, indices, hsoracle.Port().quantize(data), 0, 2048)
+    assert fmt.stats()["n_col_tiles"] >= 8 * ctas
+    rec = fmt.plan(ctas)
+    # every CTA walks its tiles upwards in steps of `ctas`
+    for c in (0, ctas // 2, ctas - 1):
+        tiles = []
+        for cta, tile, a, b in rec:
+            if int(cta) == c and (not tiles or tiles[-1] != int(tile)):
+                tiles.append(int(tile))
+        d = np.diff(tiles)
+        assert len(tiles) >= 6 and np.median(d) == ctas, (c, tiles[:8])
