@@ -78,6 +78,17 @@ benckmark_result spmv_benchmark(hsb_runtime &runtime, spmv::io::CSRMatrix<float>
               << (double)st.format_bytes / nnz << " B/nnz), algorithmic " << st.algorithmic_bytes / 1e6 << " MB" << std::endl;
     std::cout << "INFO : roofline: " << st.algorithmic_bytes / 1e6 / step_ms << " GB/s algorithmic, "
               << st.format_bytes / 1e6 / step_ms << " GB/s streamed (B200 HBM3e: 8000 spec)" << std::endl;
+    // the same loop with HOST buffers: every SpMV uploads its x and downloads its y (the transfers the
+    // reference does once, outside its timed loop, host.cpp:293-299 and :370-371), pipelined over two buffers
+    aligned_vector<VAL_T> x2(x), y0(mat.num_rows), y1(mat.num_rows);
+    const void *xs[2] = {x.data(), x2.data()};
+    void *ys[2] = {y0.data(), y1.data()};
+    double e2e_s = 0, e2e_sync_s = 0;
+    HSB_CHECK(hsb_time_e2e(runtime.ctx, xs, ys, mat.num_cols, mat.num_rows, 4 * NUM_RUNS, 1, &e2e_s));
+    HSB_CHECK(hsb_time_e2e(runtime.ctx, xs, ys, mat.num_cols, mat.num_rows, NUM_RUNS, 0, &e2e_sync_s));
+    std::cout << "INFO : with host buffers (x up, y down per SpMV): " << e2e_s * 1e3 << " ms pipelined ("
+              << 2.0 * nnz / 1e9 / e2e_s << " GOPS), " << e2e_sync_s * 1e3 << " ms synchronous ("
+              << 2.0 * nnz / 1e9 / e2e_sync_s << " GOPS)" << std::endl;
     return r;
 }
 

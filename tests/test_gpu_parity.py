@@ -626,3 +626,15 @@ def test_peer_iteration_single_rank(gpu, port):
     ctx.spmv()
     assert np.array_equal(ctx.download_result(), port.spmv_q824(ip2, indices, words, x))
     ctx.close()
+
+
+def test_cpp_benchmark_driver(gpu):
+    """hisparse_b200/host/benchmark.cpp (the mirror of sw/benchmark.cpp) on a synthetic matrix: prints the
+    reference's result line and the host-buffer pipeline line."""
+    import subprocess
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hisparse_b200", "host")
+    subprocess.run(["make", "-s", "-C", host], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(host, "bin", "benchmark_fixed"), "rmat:20000:400000:3"], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "GOPS }" in r.stdout and "with host buffers" in r.stdout and "===== Benchmark Finished =====" in r.stdout
