@@ -562,7 +562,7 @@ int hsb_upload_matrix_csr(hsb_ctx *c, uint32_t rows, uint32_t cols, const uint32
     hsb::TiledMatrix M;
     std::string err;
     if (!hsb::build_tiled(rows, cols, indptr, indices, (const uint32_t *)vals, rows_per_partition,
-                          hsb::choose_tile_cols(cols), 0, &M, &err))
+                          hsb::choose_tile_cols(cols, rows, rows ? indptr[rows] : 0), 0, &M, &err))
         return set_err(HSB_EINVAL, "malformed CSR: " + err);
     c->preprocess_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return upload_tiled(c, M);
@@ -579,7 +579,7 @@ int hsb_upload_matrix_csr_device(hsb_ctx *c, uint32_t rows, uint32_t cols, uint6
     hsb::DeviceFormat f;
     std::string err;
     cudaError_t e = hsb::build_tiled_gpu(rows, cols, nnz, d_indptr, d_indices, (const uint32_t *)d_vals,
-                                         rows_per_partition, hsb::choose_tile_cols(cols), c->stream, &M, &f, &err);
+                                         rows_per_partition, hsb::choose_tile_cols(cols, rows, nnz), c->stream, &M, &f, &err);
     if (e != cudaSuccess) {
         cudaFree(f.vals); cudaFree(f.cols); cudaFree(f.slice_rows);
         cudaGetLastError();

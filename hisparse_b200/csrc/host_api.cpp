@@ -17,7 +17,7 @@ hsb_format *hsb_format_build(uint32_t rows, uint32_t cols, const uint32_t *indpt
     hsb_format *f = new hsb_format;
     std::string err;
     if (!hsb::build_tiled(rows, cols, indptr, indices, (const uint32_t *)vals, rows_per_partition,
-                          tile_cols ? tile_cols : hsb::choose_tile_cols(cols), 0, &f->M, &err)) {
+                          tile_cols ? tile_cols : hsb::choose_tile_cols(cols, rows, rows ? indptr[rows] : 0), 0, &f->M, &err)) {
         delete f;
         return nullptr;
     }

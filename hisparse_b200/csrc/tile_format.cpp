@@ -21,13 +21,21 @@
 
 namespace hsb {
 
-uint32_t choose_tile_cols(uint32_t cols) {
+uint32_t choose_tile_cols(uint32_t cols, uint32_t rows, uint64_t nnz) {
     if (cols == 0) return 8;
     // Measured on B200: a matrix whose whole x fits the 224 KB tile limit is
-    // fastest as ONE tile (no row is cut, half the lane streams: C3 15.2 -> 12.3 us); wider
-    // matrices are fastest with tiles of at most 32768 columns, because the x staging of a tile
-    // sits on every CTA's critical path (C2: 4 tiles 16.1 us, 2 tiles 18.1 us).
-    uint32_t cap = cols <= kMaxTileCols ? kMaxTileCols : 32768u;
+    // fastest as ONE tile (no row is cut, half the lane streams: C3 15.2 -> 12.3 us). Wider matrices want
+    // narrower tiles, because the x staging of a tile sits on every CTA's critical path (C2: 2 tiles of
+    // 54 K columns 16.6 us, 3-4 tiles 15.1-15.2 us): at most 44,000 columns when rows still have a few
+    // entries per tile (longer lane streams, fewer row updates: C4 65.2 -> 62.5 us against 32,768), at most
+    // 32,768 for hypersparse matrices with less than one entry per (row, tile), where wider tiles only make
+    // the staging longer (C5 shard: 1.43 ms at 32 K, 1.81 ms at 56 K).
+    uint32_t cap = kMaxTileCols;
+    if (cols > kMaxTileCols) {
+        const uint64_t tiles44 = (cols + 44000u - 1) / 44000u;
+        const double per_row_tile = rows ? (double)nnz / ((double)rows * (double)tiles44) : 0.0;
+        cap = per_row_tile >= 1.0 ? 44000u : 32768u;
+    }
     if (const char *e = std::getenv("HSB_TILE_COLS")) {          // tuning aid
         uint32_t v = (uint32_t)std::atoi(e) & ~7u;
         if (v >= 8 && v <= kMaxTileCols) cap = v;
@@ -309,11 +317,12 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
 }
 
 // cost of finishing a slice (row-id load, warp vote, up to 32 row updates) in units of one step
-// (768 B of matrix stream); fitted to per-CTA traces on B200. HSB_SLICE_COST overrides for tuning.
+// (768 B of matrix stream); per-CTA traces fit 1.5-1.7, the measured optimum of the balance is 2.5 (C2: 15.18 -> 14.98 us).
+// HSB_SLICE_COST overrides for tuning.
 double slice_cost() {
     static const double v = [] {
         const char *e = std::getenv("HSB_SLICE_COST");
-        return e ? std::atof(e) : 1.5;
+        return e ? std::atof(e) : 2.5;
     }();
     return v;
 }

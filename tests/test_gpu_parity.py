@@ -90,7 +90,7 @@ def test_fixed_edge_cases(gpu, port):
     ix = np.concatenate([np.arange(n), [3]]).astype(np.uint32)
     d = np.full(n + 1, 0.001, np.float32)
     y, want, st = run_fixed_csr(port, (4, n, ip, ix, d), np.full(n, 0.5, np.float32))
-    assert np.array_equal(y, want) and st["n_col_tiles"] == 3     # 70000 columns: three tiles of <= 32768
+    assert np.array_equal(y, want) and st["n_col_tiles"] == 2     # 70000 columns, dense rows: two tiles of <= 44000
     y, want, _ = run_fixed_csr(port, (4, n, ip, ix, d), np.zeros(n, np.float32))
     assert np.array_equal(y, want) and not y.any()
     # reference-style x in {0,1} (sw/host.cpp:238)
