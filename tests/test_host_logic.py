@@ -173,3 +173,51 @@ def test_plan_interleaves_tiles_when_there_are_many():
                 tiles.append(int(tile))
         d = np.diff(tiles)
         assert len(tiles) >= 6 and np.median(d) == ctas, (c, tiles[:8])
+
+
+# ------------------------------------------------------------------------------------------
+# the C header as a C compiler sees it: plain C, and the same struct layouts the ctypes glue assumes
+# ------------------------------------------------------------------------------------------
+def test_header_is_plain_c_and_layouts_match_ctypes(tmp_path):
+    import ctypes
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "hisparse_b200.h"
+int main(void) {
+    printf("stats %zu %zu %zu %zu %zu\n", sizeof(hsb_stats), offsetof(hsb_stats, n_slices), offsetof(hsb_stats, format_bytes),
+           offsetof(hsb_stats, kernel_launches), offsetof(hsb_stats, preprocess_seconds));
+    printf("config %zu\n", sizeof(hsb_config));
+    printf("dcsr %zu %zu %zu %zu\n", sizeof(hsb_device_csr), offsetof(hsb_device_csr, nnz), offsetof(hsb_device_csr, d_indptr),
+           offsetof(hsb_device_csr, device));
+    printf("blob %d\n", HSB_PEER_BLOB_BYTES);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    inc = capi.HEADER.rsplit("/", 1)[0]
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = dict((l.split()[0], [int(v) for v in l.split()[1:]]) for l in
+               subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    S, D = capi.Stats, capi.DeviceCsrStruct
+    assert out["stats"] == [ctypes.sizeof(S), S.n_slices.offset, S.format_bytes.offset, S.kernel_launches.offset,
+                            S.preprocess_seconds.offset]
+    assert out["config"] == [ctypes.sizeof(capi.Config)]
+    assert out["dcsr"] == [ctypes.sizeof(D), D.nnz.offset, D.d_indptr.offset, D.device.offset]
+    assert out["blob"] == [capi.PEER_BLOB_BYTES]
+
+
+def test_tile_width_rule():
+    """one tile while x fits shared memory; <= 44,000 columns for ordinary wide matrices; <= 32,768 when there is
+    less than one entry per row and tile (hypersparse)"""
+    q = hsoracle.Port().quantize
+    r, c, ip, ix, d = matgen.random_csr(256, 57344, 0.002, 1)
+    assert capi.Format(r, c, ip, ix, q(d)).stats()["n_col_tiles"] == 1
+    r, c, ip, ix, d = matgen.random_csr(600, 107616, 0.01, 2)                  # ~1076 entries per row: dense enough
+    st = capi.Format(r, c, ip, ix, q(d)).stats()
+    assert st["n_col_tiles"] == 3 and st["tile_cols"] <= 44000
+    r, c, ip, ix, d = matgen.random_csr(4000, 400000, 0.000005, 3)             # ~2 entries per row over 10+ tiles
+    st = capi.Format(r, c, ip, ix, q(d)).stats()
+    assert st["n_col_tiles"] == 13 and st["tile_cols"] <= 32768
