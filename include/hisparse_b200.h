@@ -118,7 +118,7 @@ int hsb_spmv_row_partition(hsb_ctx *ctx, unsigned row_part_id, unsigned part_len
 
 /* all row partitions back to back (the loop at sw/benchmark.cpp:317-340), asynchronous.
  * The packed result becomes final on the device at the next hsb_sync() / hsb_download_result()
- * (or inside the next hsb_spmv*, which drains its predecessor's row accumulators first). */
+ * (or at the end of the next hsb_spmv*, whose CTAs drain their predecessor's row accumulators last). */
 int hsb_spmv(hsb_ctx *ctx);
 int hsb_sync(hsb_ctx *ctx);
 
@@ -128,7 +128,7 @@ int hsb_download_result(hsb_ctx *ctx, void *y_packed, unsigned num_rows);
 /* The same without the finish(): the copy runs on its own stream (the reference's queue is out of
  * order too, sw/host.cpp:586-590); y_packed is valid after the next hsb_sync() -- not earlier: when the
  * sums of the last SpMV are still in the row accumulators the copy is deferred and attached to the next
- * hsb_spmv (whose prologue drains them anyway) or issued by hsb_sync. Together with the double-buffered
+ * hsb_spmv (which drains them anyway, at its end) or issued by hsb_sync. Together with the multi-buffered
  * x of hsb_upload_vector and a double-buffered device y, upload(k+1), SpMV(k) and download(k-1)
  * overlap, and the compute stream carries nothing but back-to-back kernel launches. */
 int hsb_download_result_async(hsb_ctx *ctx, void *y_packed, unsigned num_rows);
@@ -187,12 +187,12 @@ int hsb_time_e2e(hsb_ctx *ctx, const void *const x_host[2], void *const y_host[2
  * page-locked memory are written by the kernel's drain itself instead of the copy engine (default). */
 int hsb_set_option(hsb_ctx *ctx, const char *name, int value);
 /* Profiling aid: SM-clock stamps of the last launch, [sm_count][34] = per warp "my slices are done",
- * then CTA "arrived at the grid barrier", then "drain done". out == NULL arms (capacity != 0) or
+ * then CTA "finished" (wait for the predecessor and drain included); the last word is unused. out == NULL arms (capacity != 0) or
  * disarms (capacity == 0) the trace and returns the number of words. */
 int hsb_debug_trace(hsb_ctx *ctx, unsigned long long *out, size_t capacity);
 /* Profiling aid: %globaltimer stamps (ns) of the last 256 SpMV launches, [256][8] indexed by launch number
  * % 256: 0 first CTA started, 1 CTA 0 saw its x flag, 2 CTA 0 saw the predecessor complete, 3 CTA 0 finished
- * its drain share, 4 CTA 0 has its x tile, 5 last CTA ended. out == NULL arms (capacity != 0) / disarms.
+ * its drain share and published it, 4 CTA 0 has its x tile, 5 last CTA ended, 6 CTA 0 finished its matrix work. out == NULL arms (capacity != 0) / disarms.
  * Returns the number of the last launch. */
 int hsb_debug_timeline(hsb_ctx *ctx, unsigned long long *out, size_t capacity);
 /* Profiling aid: steps and slices the whole-matrix plan gives to every CTA. */
