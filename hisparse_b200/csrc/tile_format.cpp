@@ -316,15 +316,33 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
     return true;
 }
 
-// cost of finishing a slice (row-id load, warp vote, up to 32 row updates) in units of one step
-// (768 B of matrix stream); per-CTA traces fit 1.5-1.7, the measured optimum of the balance is 2.5 (C2: 15.18 -> 14.98 us).
-// HSB_SLICE_COST overrides for tuning.
-double slice_cost() {
-    static const double v = [] {
+// Cost of finishing a slice (row-id load, warp vote, up to 32 row updates) in units of one step (768 B of
+// matrix stream) for the equal-cost cuts of the planner. Per-CTA traces fit 1.5-1.7 steps, but what the cuts
+// have to balance is the END of a length-sorted tile, where slices are one or two steps long and a warp is
+// bound by the latency of a slice rather than by its bytes. Measured optimum (B200, final kernel): C2 (11.6
+// steps per slice on average) 15.0 us at 2.5, 14.05 us at 6-8, 14.6 us at 15; C4 (3.1 steps per slice) 64.1 us
+// at 2.5, 67.4 us at 6. The rule that fits both: 0.6 x the average steps per slice of the launch, within
+// [2.5, 8]. HSB_SLICE_COST overrides it.
+namespace {
+thread_local double g_slice_cost = 2.5;
+}
+double slice_cost() { return g_slice_cost; }
+static void set_slice_cost_for(const TiledMatrix &m, uint32_t tile_begin, uint32_t tile_end) {
+    static const double forced = [] {
         const char *e = std::getenv("HSB_SLICE_COST");
-        return e ? std::atof(e) : 2.5;
+        return e ? std::atof(e) : 0.0;
     }();
-    return v;
+    if (forced > 0.0) { g_slice_cost = forced; return; }
+    uint64_t steps = 0, slices = 0;
+    for (uint32_t t = tile_begin; t < tile_end; t++) {
+        const TileDesc &td = m.tiles[t];
+        if (td.slice_end == td.slice_begin) continue;
+        const SliceDesc &last = m.slices[td.slice_end - 1];
+        steps += last.off + (last.tile_steps & 0xFFu) - td.step_begin;
+        slices += td.slice_end - td.slice_begin;
+    }
+    const double avg = slices ? (double)steps / (double)slices : 1.0;
+    g_slice_cost = std::min(8.0, std::max(2.5, 0.6 * avg));
 }
 namespace {
 // tile-relative step position at which the cost prefix (steps + kSliceCost * slices started) of
@@ -394,6 +412,7 @@ Segment make_segment(const TiledMatrix &m, uint32_t tile, uint32_t t_lo, uint32_
 void plan_launch(const TiledMatrix &m, uint32_t tile_begin, uint32_t tile_end, uint32_t ctas,
                  std::vector<uint32_t> *cta_seg, std::vector<Segment> *segs) {
     cta_seg->assign(ctas + 1, (uint32_t)segs->size());
+    set_slice_cost_for(m, tile_begin, tile_end);
     std::vector<uint32_t> live;
     std::vector<double> cost;
     double total = 0;

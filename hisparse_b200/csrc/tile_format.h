@@ -122,7 +122,8 @@ static_assert(sizeof(Segment) % 16 == 0, "Segment is loaded with 128-bit loads")
 // segs[cta_seg[b] .. cta_seg[b+1]). Cuts are placed at equal cost (steps + one unit per slice,
 // the latter paying for the slice's 32 row updates) and may fall inside a slice; when there are
 // no more tiles than CTAs no CTA works on two tiles (a second x staging would double its time).
-// cost of finishing a slice in units of one step (HSB_SLICE_COST overrides the fitted default)
+// cost of finishing a slice in units of one step, as set by the last plan_launch of this thread
+// (0.6 x the average steps per slice, within [2.5, 8]; HSB_SLICE_COST overrides)
 double slice_cost();
 void plan_launch(const TiledMatrix &m, uint32_t tile_begin, uint32_t tile_end, uint32_t ctas,
                  std::vector<uint32_t> *cta_seg, std::vector<Segment> *segs);
