@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -322,7 +323,8 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
 // bound by the latency of a slice rather than by its bytes. Measured optimum (B200, final kernel): C2 (11.6
 // steps per slice on average) 15.0 us at 2.5, 14.05 us at 6-8, 14.6 us at 15; C4 (3.1 steps per slice) 64.1 us
 // at 2.5, 67.4 us at 6. The rule that fits both: 0.6 x the average steps per slice of the launch, within
-// [2.5, 8]. HSB_SLICE_COST overrides it.
+// [2.5, 8], when at least a quarter of the slices are one or two steps long; 2.5 otherwise. HSB_SLICE_COST
+// overrides it, HSB_DEBUG_PLAN prints the choice.
 namespace {
 thread_local double g_slice_cost = 2.5;
 }
@@ -333,16 +335,24 @@ static void set_slice_cost_for(const TiledMatrix &m, uint32_t tile_begin, uint32
         return e ? std::atof(e) : 0.0;
     }();
     if (forced > 0.0) { g_slice_cost = forced; return; }
-    uint64_t steps = 0, slices = 0;
+    uint64_t steps = 0, slices = 0, short_slices = 0;
     for (uint32_t t = tile_begin; t < tile_end; t++) {
         const TileDesc &td = m.tiles[t];
         if (td.slice_end == td.slice_begin) continue;
         const SliceDesc &last = m.slices[td.slice_end - 1];
         steps += last.off + (last.tile_steps & 0xFFu) - td.step_begin;
         slices += td.slice_end - td.slice_begin;
+        short_slices += (td.slice_end - td.slice_begin) - td.cnt_ge[2];        // slices of one or two steps
     }
     const double avg = slices ? (double)steps / (double)slices : 1.0;
-    g_slice_cost = std::min(8.0, std::max(2.5, 0.6 * avg));
+    // Only a mix of long and short slices needs the higher cost; when (nearly) all slices are long -- the
+    // pruned transformer layers: every slice 32 steps -- the cuts inside a CTA should stay close to equal steps.
+    const bool mixed = slices && (double)short_slices >= 0.25 * (double)slices;
+    g_slice_cost = mixed ? std::min(8.0, std::max(2.5, 0.6 * avg)) : 2.5;
+    static const bool debug = std::getenv("HSB_DEBUG_PLAN") != nullptr;
+    if (debug)
+        std::fprintf(stderr, "[hsb plan] tiles %u..%u: %llu slices, %.2f steps per slice, %.0f %% of one or two steps -> slice cost %.2f\n",
+                     tile_begin, tile_end, (unsigned long long)slices, avg, slices ? 100.0 * short_slices / slices : 0.0, g_slice_cost);
 }
 namespace {
 // tile-relative step position at which the cost prefix (steps + kSliceCost * slices started) of
