@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -22,6 +23,8 @@
 namespace {
 
 thread_local std::string g_err;
+// bumped by hsb_host_free: cached "this host pointer is page-locked" answers may be stale afterwards
+std::atomic<unsigned> g_host_free_generation{0};
 
 int set_err(int code, const std::string &m) { g_err = m; return code; }
 
@@ -151,7 +154,7 @@ struct hsb_ctx {
     struct { void *host = nullptr; uint32_t *dev = nullptr; unsigned n = 0; bool active = false; } pending_dl;
     const void *pin_cache_host[4] = {nullptr, nullptr, nullptr, nullptr};   // small cache of cudaPointerGetAttributes results
     uint32_t *pin_cache_dev[4] = {nullptr, nullptr, nullptr, nullptr};
-    unsigned pin_cache_next = 0;
+    unsigned pin_cache_next = 0, pin_cache_generation = 0;
     // rows + 1 accumulators (uint64 fixed / fp32 float) x 4 in rotation: launch n adds into buffer n % 4 and,
     // at its very end, drains buffer (n - 1) % 4 (its predecessor's sums) into y and re-zeroes it. Four, because
     // consecutive launches overlap freely (see the kernel): buffer n % 4 is reused by launch n + 4, which
@@ -290,6 +293,11 @@ int finish(hsb_ctx *c);
 
 // device alias of a page-locked, mapped host buffer (hsb_host_alloc), or null for pageable memory
 uint32_t *mapped_alias(hsb_ctx *c, const void *host) {
+    const unsigned gen = g_host_free_generation.load(std::memory_order_relaxed);
+    if (gen != c->pin_cache_generation) {
+        for (int i = 0; i < 4; i++) { c->pin_cache_host[i] = nullptr; c->pin_cache_dev[i] = nullptr; }
+        c->pin_cache_generation = gen;
+    }
     for (int i = 0; i < 4; i++)
         if (c->pin_cache_host[i] == host) return c->pin_cache_dev[i];
     cudaPointerAttributes at;
@@ -301,9 +309,9 @@ uint32_t *mapped_alias(hsb_ctx *c, const void *host) {
     return dev;
 }
 
-// A launch's completion is normally announced by its successor's prologue. When there may be no
-// successor (hsb_sync, a second upload in a row, ...) the compute stream announces everything launched
-// so far itself, with a stream memory operation behind the last kernel.
+// A launch's completion is normally announced by its successor (after the griddepcontrol.wait at the end of
+// its CTA 0). When there may be no successor (hsb_sync, a second upload in a row, ...) the compute stream
+// announces everything launched so far itself, with a stream memory operation behind the last kernel.
 int publish_done(hsb_ctx *c) {
     if (c->publish_sure == c->launch_seq) return HSB_OK;
     MEMOP_TRY(g_write32((CUstream)c->stream, (CUdeviceptr)c->d_done, c->launch_seq, 0));
@@ -550,7 +558,11 @@ void *hsb_host_alloc(size_t bytes) {
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
-void hsb_host_free(void *p) { if (p) cudaFreeHost(p); }
+void hsb_host_free(void *p) {
+    if (!p) return;
+    g_host_free_generation.fetch_add(1, std::memory_order_relaxed);
+    cudaFreeHost(p);
+}
 
 int hsb_upload_matrix_csr(hsb_ctx *c, uint32_t rows, uint32_t cols, const uint32_t *indptr,
                           const uint32_t *indices, const void *vals, uint32_t rows_per_partition) {
