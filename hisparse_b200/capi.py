@@ -125,6 +125,7 @@ def lib():
     L.hsb_format_expand.argtypes = [vp, vp, vp, vp]
     L.hsb_format_plan.argtypes = [vp, u32, vp, sz]
     L.hsb_format_plan.restype = C.c_longlong
+    L.hsb_format_emulate_fixed.argtypes = [vp, u32, vp, vp]
     L.hsb_format_free.argtypes = [vp]
     L.hsb_format_free.restype = None
     L.hsb_cpsr_to_csr.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(sz), C.c_uint, C.c_uint, C.c_uint, C.c_uint,
@@ -429,6 +430,13 @@ class Format:
         rec = np.zeros((max(n, 1), 4), np.uint32)
         lib().hsb_format_plan(self.h, ctas, _ptr(rec), n)
         return rec[:n]
+
+    def emulate_fixed(self, ctas, x_words):
+        """host walk of the launch plan the way the kernel executes it (test aid) -> y words"""
+        x_words = _words(x_words)
+        y = np.zeros(self.rows, np.uint32)
+        _check(lib().hsb_format_emulate_fixed(self.h, ctas, _ptr(x_words), _ptr(y)))
+        return y
 
     def expand(self):
         indptr = np.zeros(self.rows + 1, np.uint32)

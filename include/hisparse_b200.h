@@ -245,6 +245,10 @@ int hsb_format_expand(const hsb_format *f, uint32_t *indptr, uint32_t *indices, 
  * {cta, tile, first step, end step} with tile-relative steps. Returns the number of records (call with
  * records == NULL to size the buffer). Every step of every tile is covered exactly once. */
 long long hsb_format_plan(const hsb_format *f, uint32_t ctas, uint32_t *records, size_t capacity_records);
+/* y = A x (fixed point) computed on the HOST by walking that plan exactly as the kernel does (segments, warp
+ * shares, slice geometry from the tile tables, per-lane sums handed to slice_rows): checks the contract between
+ * formatter, planner and kernel without a GPU. Test aid, not a compute path: single thread, no vectorisation. */
+int hsb_format_emulate_fixed(const hsb_format *f, uint32_t ctas, const uint32_t *x_words, uint32_t *y_words);
 void hsb_format_free(hsb_format *f);
 /* Decode reference channel images back to CSR (what hsb_upload_matrix_cpsr does first).
  * indptr: num_rows + 1 words; indices / vals: capacity words each; *nnz receives the count

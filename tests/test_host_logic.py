@@ -221,3 +221,36 @@ def test_tile_width_rule():
     r, c, ip, ix, d = matgen.random_csr(4000, 400000, 0.000005, 3)             # ~2 entries per row over 10+ tiles
     st = capi.Format(r, c, ip, ix, q(d)).stats()
     assert st["n_col_tiles"] == 13 and st["tile_cols"] <= 32768
+
+
+# ------------------------------------------------------------------------------------------
+# the formatter / planner / kernel contract, walked on the host (hsb_format_emulate_fixed)
+# ------------------------------------------------------------------------------------------
+EMU_CASES = [
+    ("dense128", lambda: matgen.dense_csr(128, 128), 0, 0, 148),
+    ("uniform_unsorted", lambda: matgen.uniform_sparse_csr(1000, 1024, 10), 0, 0, 148),
+    ("rmat_one_tile", lambda: matgen.rmat_csr(6000, 150000, 5), 0, 0, 148),
+    ("rmat_few_ctas", lambda: matgen.rmat_csr(6000, 150000, 5), 0, 0, 7),
+    ("rmat_two_ctas_per_sm", lambda: matgen.rmat_csr(20000, 500000, 6), 0, 0, 296),
+    ("multi_tile", lambda: matgen.random_csr(900, 70000, 0.004, 7), 0, 16384, 148),
+    ("many_tiles_interleaved", lambda: matgen.random_csr(2000, 400000, 0.0004, 9), 0, 1024, 37),
+    ("row_partitions", lambda: matgen.rmat_csr(20000, 300000, 9), 4096, 0, 148),
+    ("hypersparse_singletons", lambda: matgen.random_csr(30000, 3000000, 0.000004, 13), 0, 32768, 148),
+    ("long_row_two_tiles", lambda: (4, 70000, np.array([0, 0, 70000, 70000, 70001], np.uint32),
+                                    np.concatenate([np.arange(70000), [3]]).astype(np.uint32),
+                                    np.full(70001, 0.001, np.float32)), 0, 0, 148),
+    ("saturating", lambda: matgen.random_csr(256, 4096, 0.3, 15), 0, 0, 64),
+]
+
+
+@pytest.mark.parametrize("name,make,rpp,tile_cols,ctas", EMU_CASES, ids=[c[0] for c in EMU_CASES])
+def test_plan_walk_matches_oracle(port, name, make, rpp, tile_cols, ctas):
+    rows, cols, indptr, indices, data = make()
+    scale = 40.0 if name == "saturating" else 1.0          # row sums beyond 2^32 - 1: the clamp must show
+    words = port.quantize((data * np.float32(scale)).astype(np.float32))
+    x = port.quantize(np.random.default_rng(1).random(cols, dtype=np.float32) * np.float32(scale))
+    fmt = capi.Format(rows, cols, indptr, indices, words, rpp, tile_cols)
+    want = port.spmv_q824(indptr, indices, words, x)
+    assert np.array_equal(fmt.emulate_fixed(ctas, x), want)
+    if name == "saturating":
+        assert (want == 0xFFFFFFFF).any()
