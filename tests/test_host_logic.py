@@ -254,3 +254,16 @@ def test_plan_walk_matches_oracle(port, name, make, rpp, tile_cols, ctas):
     assert np.array_equal(fmt.emulate_fixed(ctas, x), want)
     if name == "saturating":
         assert (want == 0xFFFFFFFF).any()
+
+
+def test_plan_walk_bench_matrix(port):
+    """the bench line's own matrix (C2 stand-in, 13.6 M non-zeros) on the bench line's own plan (148 CTAs, three
+    x tiles, the mixed-slice cost rule): the host walk reproduces the oracle bit for bit, saturated row included"""
+    import bench
+    bench.WORKLOAD = "c2"
+    r2, c2, ip2, indices, data, x = bench.workload(0)
+    words, xw = matgen.quantize_q824(data), matgen.quantize_q824(x)
+    fmt = capi.Format(r2, c2, ip2, indices, words)
+    assert fmt.stats()["n_col_tiles"] == 3
+    want = port.spmv_q824(ip2, indices, words, xw)
+    assert np.array_equal(fmt.emulate_fixed(148, xw), want)
