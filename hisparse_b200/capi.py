@@ -19,7 +19,7 @@ HEADER = os.path.join(ROOT, "include", "hisparse_b200.h")
 IMPL_FIXED, IMPL_FLOAT_POB, IMPL_FLOAT_STALL = 0, 1, 2
 IMPL_BY_NAME = {"fixed": 0, "float_pob": 1, "float_stall": 2}
 NUM_HBM_CHANNELS, PACK_SIZE = 16, 8
-PEER_BLOB_BYTES = 160
+PEER_BLOB_BYTES = 192
 
 
 class HsbError(RuntimeError):
@@ -114,6 +114,13 @@ def lib():
     L.hsb_peer_export.argtypes = [vp, vp]
     L.hsb_peer_connect.argtypes = [vp, C.c_int, C.c_int, vp]
     L.hsb_axpb_to_peers.argtypes = [vp, u32, u32, u32]
+    L.hsb_gather_export.argtypes = [vp, u32, C.c_int, vp]
+    L.hsb_gather_connect.argtypes = [vp, C.c_int, C.c_int, u32, vp]
+    L.hsb_gather_wait.argtypes = [vp]
+    L.hsb_device_y_gathered.argtypes = [vp]
+    L.hsb_device_y_gathered.restype = vp
+    L.hsb_download_gathered.argtypes = [vp, vp, u32]
+    L.hsb_device_numa_node.argtypes = [C.c_int]
     L.hsb_debug_trace.argtypes = [vp, vp, sz]
     L.hsb_debug_timeline.argtypes = [vp, vp, sz]
     L.hsb_debug_plan.argtypes = [vp, vp, vp, sz]
@@ -125,7 +132,6 @@ def lib():
     L.hsb_format_expand.argtypes = [vp, vp, vp, vp]
     L.hsb_format_plan.argtypes = [vp, u32, vp, sz]
     L.hsb_format_plan.restype = C.c_longlong
-    L.hsb_format_emulate_fixed.argtypes = [vp, u32, vp, vp]
     L.hsb_format_free.argtypes = [vp]
     L.hsb_format_free.restype = None
     L.hsb_cpsr_to_csr.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(sz), C.c_uint, C.c_uint, C.c_uint, C.c_uint,
@@ -146,13 +152,20 @@ def _check(rc):
 
 
 def _words(a):
-    """any 32-bit array (uint32 / float32) -> contiguous uint32 view"""
+    """32-bit words for the C ABI: float32 and (u)int32 arrays are reinterpreted, wider INTEGER arrays (index
+    arrays such as scipy's int64 indptr) are range-checked and narrowed. Anything else -- float64 above all,
+    scipy's default value dtype -- is refused: converting it here would silently truncate 0.5 to 0."""
     a = np.ascontiguousarray(a)
-    if a.dtype == np.float32:
+    if a.dtype == np.uint32:
+        return a
+    if a.dtype in (np.float32, np.int32):
         return a.view(np.uint32)
-    if a.dtype != np.uint32:
-        a = a.astype(np.uint32)
-    return a
+    if np.issubdtype(a.dtype, np.integer):
+        if a.size and (int(a.min()) < 0 or int(a.max()) > 0xFFFFFFFF):
+            raise ValueError("index array does not fit 32 bits")
+        return a.astype(np.uint32)
+    raise TypeError("expected 32-bit words (float32 values, or raw uint32 Q8.24 words), got %s: convert explicitly "
+                    "(x.astype(np.float32), or matgen.quantize_q824 for the fixed-point path)" % a.dtype)
 
 
 def _ptr(a):
@@ -339,6 +352,29 @@ class Context:
     def axpb_to_peers(self, alpha_word, beta_word, col_offset):
         _check(lib().hsb_axpb_to_peers(self.h, int(alpha_word), int(beta_word), col_offset))
 
+    def gather_export(self, total_rows, want_buffer=True):
+        blob = np.zeros(PEER_BLOB_BYTES, np.uint8)
+        _check(lib().hsb_gather_export(self.h, total_rows, 1 if want_buffer else 0, _ptr(blob)))
+        self.gather_rows = total_rows
+        return blob
+
+    def gather_connect(self, world, rank, row_offset, blobs):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8)
+        assert blobs.size == world * PEER_BLOB_BYTES
+        _check(lib().hsb_gather_connect(self.h, world, rank, row_offset, _ptr(blobs)))
+
+    def gather_wait(self):
+        _check(lib().hsb_gather_wait(self.h))
+
+    def device_y_gathered(self):
+        return lib().hsb_device_y_gathered(self.h)
+
+    def download_gathered(self, out=None):
+        if out is None:
+            out = np.empty(self.gather_rows, np.uint32)
+        _check(lib().hsb_download_gathered(self.h, _ptr(out), out.size))
+        return out
+
     def iterate(self, iters, alpha_word, beta_word):
         """iters x { x <- alpha (*) A x (+) beta } on the device (PageRank-style power iteration)"""
         _check(lib().hsb_iterate(self.h, iters, int(alpha_word), int(beta_word)))
@@ -412,6 +448,7 @@ class Format:
     def __init__(self, rows, cols, indptr, indices, vals, rows_per_partition=0, tile_cols=0):
         indptr, indices, vals = _words(indptr), _words(indices), _words(vals)
         self.rows, self.nnz = rows, int(indptr[-1]) if indptr.size else 0
+        self._csr = (rows, cols, indptr, indices, vals, rows_per_partition, tile_cols)
         self.h = lib().hsb_format_build(rows, cols, _ptr(indptr), _ptr(indices), _ptr(vals), rows_per_partition,
                                         tile_cols)
         if not self.h:
@@ -435,7 +472,11 @@ class Format:
         """host walk of the launch plan the way the kernel executes it (test aid) -> y words"""
         x_words = _words(x_words)
         y = np.zeros(self.rows, np.uint32)
-        _check(lib().hsb_format_emulate_fixed(self.h, ctas, _ptr(x_words), _ptr(y)))
+        rows, cols, indptr, indices, vals, rpp, tile_cols = self._csr
+        rc = _plancheck().hsbt_emulate_fixed(rows, cols, _ptr(indptr), _ptr(indices), _ptr(vals), rpp, tile_cols, ctas,
+                                             _ptr(x_words), _ptr(y))
+        if rc != 0:
+            raise HsbError("the host walk of the launch plan found an inconsistency (%d)" % rc)
         return y
 
     def expand(self):
@@ -450,6 +491,22 @@ class Format:
             lib().hsb_format_free(self.h)
         except Exception:
             pass
+
+
+_plan_lib = None
+
+
+def _plancheck():
+    """test aid built by hisparse_b200/host/Makefile (not part of the product library)"""
+    global _plan_lib
+    if _plan_lib is None:
+        path = os.path.join(HERE, "host", "bin", "libhsb_plancheck.so")
+        if not os.path.exists(path):
+            subprocess.run(["make", "-s", "-C", os.path.join(HERE, "host"), path], check=True, stdout=subprocess.DEVNULL)
+        _plan_lib = C.CDLL(path)
+        u32, vp = C.c_uint32, C.c_void_p
+        _plan_lib.hsbt_emulate_fixed.argtypes = [u32, u32, vp, vp, vp, u32, u32, u32, vp, vp]
+    return _plan_lib
 
 
 def cpsr_to_csr(impl, images, n_row_parts, n_col_parts, rows, cols):

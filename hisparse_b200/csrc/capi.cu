@@ -11,8 +11,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
+
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "cpsr_decode.h"
 #include "format_handle.h"
@@ -23,8 +28,11 @@
 namespace {
 
 thread_local std::string g_err;
-// bumped by hsb_host_free: cached "this host pointer is page-locked" answers may be stale afterwards
-std::atomic<unsigned> g_host_free_generation{0};
+// Page-locked host buffers handed out by hsb_host_alloc: base -> bytes. Only these are ever used as mapped
+// destinations of the drain's posted writes -- memory pinned by somebody else (torch, cudaHostRegister) can be
+// unpinned behind our back and takes the copy-engine path.
+std::mutex g_host_mu;
+std::map<uintptr_t, size_t> g_host_allocs;
 
 int set_err(int code, const std::string &m) { g_err = m; return code; }
 
@@ -108,15 +116,16 @@ struct hsb_ctx {
     std::vector<uint32_t> plan_steps, plan_slices;   // slot 0: steps / slices started per CTA (profiling aid)
     uint32_t smem_bytes = 0;              // dynamic shared memory a launch needs: widest x tile + the zero words
     // vectors
-    // x is double buffered so that the upload of the next vector (copy stream) overlaps the SpMV that
-    // still reads the current one; x_words words each (padded to whole tiles, zero filled)
-    // (three buffers in flag-pipeline mode, so that an upload never has to wait for the launch in flight)
+    // x is multi-buffered so that the upload of the next vector (copy stream) overlaps the SpMV that still
+    // reads the current one; x_words words each (padded to whole tiles, zero filled). Event mode rotates two
+    // buffers, the flag pipeline four, so that an upload never has to wait for the launch in flight.
     uint32_t *d_x[kXBuffers] = {nullptr, nullptr, nullptr, nullptr};   // slices of ONE allocation (d_x[0]): one IPC handle
     // multi-GPU iteration over peer memory (hsb_peer_connect): next-x buffers and arrival flags of every rank
     uint32_t *d_peer = nullptr;           // [0..15] arrival flags written by the ranks, [32] completion ticket
     int peer_world = 0, peer_rank = 0;
     uint32_t *peer_x[hsb::kMaxPeers] = {};     // rank g's d_x[0] (this process's own pointer for g == rank)
     uint32_t *peer_flags[hsb::kMaxPeers] = {}; // rank g's d_peer
+    bool peer_ipc[hsb::kMaxPeers] = {};        // opened through CUDA IPC (another process): closed on disconnect
     size_t x_stride = 0;                  // words between consecutive x buffers
     uint32_t peer_seq = 0;
     int x_latest = 0;                     // buffer the next launch reads
@@ -152,9 +161,16 @@ struct hsb_ctx {
     uint32_t dl_seq = 0, y_dl_seq[2] = {0, 0};   // downloads so far; value y_free[b] reaches when d_y[b] has been read out
     // deferred download; dev != null: `host` is page-locked and mapped, the next launch drains straight into it
     struct { void *host = nullptr; uint32_t *dev = nullptr; unsigned n = 0; bool active = false; } pending_dl;
-    const void *pin_cache_host[4] = {nullptr, nullptr, nullptr, nullptr};   // small cache of cudaPointerGetAttributes results
-    uint32_t *pin_cache_dev[4] = {nullptr, nullptr, nullptr, nullptr};
-    unsigned pin_cache_next = 0, pin_cache_generation = 0;
+    // gather of y across row-block shards (hsb_gather_export / hsb_gather_connect)
+    uint32_t *d_gather_y = nullptr;       // this rank's gathered result (total rows of all shards), when it is a target
+    uint32_t *d_gather_flags = nullptr;   // [0..15] arrival flags written by the ranks, [32] this rank's completion ticket
+    hsb::GatherTargets *d_gather = nullptr;   // device table the drains read, or null: no gather
+    uint32_t gather_total_rows = 0, gather_seq = 0;
+    int gather_world = 0, gather_rank = 0;
+    bool gather_is_target = false;
+    void *gather_opened[2 * hsb::kMaxPeers] = {};   // IPC mappings to close
+    int gather_n_opened = 0;
+    bool acquire = true;                  // flag waits of the kernels end in an acquire fence (hsb_set_option "acquire")
     // rows + 1 accumulators (uint64 fixed / fp32 float) x 4 in rotation: launch n adds into buffer n % 4 and,
     // at its very end, drains buffer (n - 1) % 4 (its predecessor's sums) into y and re-zeroes it. Four, because
     // consecutive launches overlap freely (see the kernel): buffer n % 4 is reused by launch n + 4, which
@@ -172,12 +188,30 @@ struct hsb_ctx {
 
 namespace {
 
+void close_peers(hsb_ctx *c) {
+    for (int g = 0; g < hsb::kMaxPeers; g++) {
+        if (c->peer_ipc[g]) {
+            if (c->peer_x[g]) cudaIpcCloseMemHandle(c->peer_x[g]);
+            if (c->peer_flags[g]) cudaIpcCloseMemHandle(c->peer_flags[g]);
+        }
+        c->peer_x[g] = nullptr; c->peer_flags[g] = nullptr; c->peer_ipc[g] = false;
+    }
+    c->peer_world = 0;
+}
+
+void close_gather(hsb_ctx *c) {
+    for (int i = 0; i < c->gather_n_opened; i++) cudaIpcCloseMemHandle(c->gather_opened[i]);
+    c->gather_n_opened = 0;
+    cudaFree(c->d_gather); cudaFree(c->d_gather_y); cudaFree(c->d_gather_flags);
+    c->d_gather = nullptr; c->d_gather_y = nullptr; c->d_gather_flags = nullptr;
+    c->gather_world = 0; c->gather_seq = 0; c->gather_total_rows = 0; c->gather_is_target = false;
+}
+
 void free_matrix(hsb_ctx *c) {
     for (auto &m : c->mats) m.release();
     c->mats.clear();
-    for (int g = 0; g < c->peer_world; g++)
-        if (g != c->peer_rank) { if (c->peer_x[g]) cudaIpcCloseMemHandle(c->peer_x[g]); if (c->peer_flags[g]) cudaIpcCloseMemHandle(c->peer_flags[g]); }
-    c->peer_world = 0;
+    close_peers(c);
+    close_gather(c);
     cudaFree(c->d_x[0]); cudaFree(c->d_peer); c->d_peer = nullptr;
     for (int b = 0; b < kXBuffers; b++) { c->d_x[b] = nullptr; c->x_reader_seq[b] = 0; }
     for (int b = 0; b < kAccBuffers; b++) { cudaFree(c->d_acc[b]); c->d_acc[b] = nullptr; }
@@ -291,22 +325,65 @@ int install_matrix(hsb_ctx *c, const hsb::TiledMatrix &M, const DeviceMatrix &d,
 
 int finish(hsb_ctx *c);
 
-// device alias of a page-locked, mapped host buffer (hsb_host_alloc), or null for pageable memory
-uint32_t *mapped_alias(hsb_ctx *c, const void *host) {
-    const unsigned gen = g_host_free_generation.load(std::memory_order_relaxed);
-    if (gen != c->pin_cache_generation) {
-        for (int i = 0; i < 4; i++) { c->pin_cache_host[i] = nullptr; c->pin_cache_dev[i] = nullptr; }
-        c->pin_cache_generation = gen;
+// NUMA node the GPU hangs off (sysfs, through its PCI bus id), or -1 when the platform does not say
+int device_numa_node(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char *q = bus; *q; q++) if (*q >= 'A' && *q <= 'Z') *q = (char)(*q - 'A' + 'a');
+    char path[128];
+    std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = std::fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (std::fscanf(f, "%d", &node) != 1) node = -1;
+    std::fclose(f);
+    return node;
+}
+
+// Page-locked buffers are faulted in by the allocation itself, on the node the calling thread's memory policy
+// prefers: prefer the node of the thread's CURRENT device while allocating (set_mempolicy through the raw
+// system call: no libnuma in this image), so that every x upload and y download of a rank crosses only its
+// own root complex.
+struct PreferDeviceNode {
+    bool active = false;
+    PreferDeviceNode() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+        const int node = device_numa_node(dev);
+        if (node < 0 || node >= 1024) return;
+        unsigned long mask[16] = {0};
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        active = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, 1025ul) == 0;
     }
-    for (int i = 0; i < 4; i++)
-        if (c->pin_cache_host[i] == host) return c->pin_cache_dev[i];
-    cudaPointerAttributes at;
-    uint32_t *dev = nullptr;
-    if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost) dev = (uint32_t *)at.devicePointer;
-    else cudaGetLastError();
-    const unsigned slot = c->pin_cache_next++ & 3u;
-    c->pin_cache_host[slot] = host; c->pin_cache_dev[slot] = dev;
-    return dev;
+    ~PreferDeviceNode() { if (active) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul); }
+};
+
+// device alias of a page-locked, mapped host buffer from hsb_host_alloc (n_words must fit inside it), or null
+uint32_t *mapped_alias(hsb_ctx *c, const void *host, size_t n_words) {
+    (void)c;
+    const uintptr_t h = (uintptr_t)host;
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        auto it = g_host_allocs.upper_bound(h);
+        if (it == g_host_allocs.begin()) return nullptr;
+        --it;
+        if (h + n_words * 4 > it->first + it->second) return nullptr;
+    }
+    void *dev = nullptr;
+    if (cudaHostGetDevicePointer(&dev, const_cast<void *>(host), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (uint32_t *)dev;
+}
+
+// a kernel gave up waiting for a flag: report it once (the launch skipped its row updates, y is incomplete)
+int check_error_flag(hsb_ctx *c) {
+    uint32_t err = 0;
+    CUDA_TRY(cudaMemcpy(&err, c->d_flags + kFlagError, 4, cudaMemcpyDeviceToHost));
+    if (err) {
+        CUDA_TRY(cudaMemset(c->d_flags + kFlagError, 0, 4));
+        return set_err(HSB_ECUDA, "a kernel gave up waiting for a flag (vector upload, result download, peer slice or "
+                                  "accumulator reuse) and skipped its row updates: the result is incomplete");
+    }
+    return HSB_OK;
 }
 
 // A launch's completion is normally announced by its successor (after the griddepcontrol.wait at the end of
@@ -393,6 +470,8 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
     }
     p.acc = c->d_acc[c->acc_cur];
     p.drain_acc = c->drain_pending ? c->d_acc[(c->acc_cur + c->acc_bufs - 1) % c->acc_bufs] : nullptr;
+    p.acquire = c->acquire ? 1u : 0u;
+    if (c->d_gather && c->drain_pending) { p.gather = c->d_gather; p.gather_seq = ++c->gather_seq; }
     p.drain_begin = c->drain_begin; p.drain_end = c->drain_end;
     p.trash_row = c->rows;
     p.trace = c->d_trace;
@@ -435,8 +514,9 @@ int finish(hsb_ctx *c) {
                 CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_ydone, 0));
             c->y_busy[yb] = false;
         }
+        const uint32_t gseq = c->d_gather ? ++c->gather_seq : 0;
         CUDA_TRY(hsb::launch_drain(c->arith, c->d_acc[(c->acc_cur + c->acc_bufs - 1) % c->acc_bufs], c->d_y[yb], c->drain_begin, c->drain_end, c->rows,
-                                   c->stream));
+                                   c->d_gather, gseq, c->stream));
         c->launches++;
         c->drain_pending = false;
     }
@@ -457,7 +537,7 @@ int quiesce(hsb_ctx *c) {
     CUDA_TRY(cudaStreamSynchronize(c->s_h2d_b));
     CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
     c->y_busy[0] = c->y_busy[1] = false;
-    return HSB_OK;
+    return check_error_flag(c);
 }
 
 int run_all(hsb_ctx *c, cudaEvent_t k0, cudaEvent_t k1) { return run_slot(c, 0, 0, c->rows, k0, k1); }
@@ -516,7 +596,7 @@ hsb_ctx *hsb_create(int device, int impl) {
     cudaEvent_t *evs[] = {&c->ev_xready, &c->ev_xfree[0], &c->ev_xfree[1], &c->ev_yready, &c->ev_ydone};
     for (cudaEvent_t *ev : evs)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = hsb::configure_kernels();
+    if (e == cudaSuccess) e = hsb::configure_kernels(prop.multiProcessorCount);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_flags, kNumFlags * 4);
     if (e == cudaSuccess) e = cudaMemset(c->d_flags, 0, kNumFlags * 4);
     if (e == cudaSuccess && load_memops()) {
@@ -555,12 +635,21 @@ void hsb_destroy(hsb_ctx *c) {
 
 void *hsb_host_alloc(size_t bytes) {
     void *p = nullptr;
-    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (!bytes) bytes = 1;
+    {
+        PreferDeviceNode numa;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    g_host_allocs[(uintptr_t)p] = bytes;
     return p;
 }
 void hsb_host_free(void *p) {
     if (!p) return;
-    g_host_free_generation.fetch_add(1, std::memory_order_relaxed);
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        g_host_allocs.erase((uintptr_t)p);
+    }
     cudaFreeHost(p);
 }
 
@@ -681,7 +770,7 @@ int hsb_upload_vector(hsb_ctx *c, const void *x_packed, unsigned num_cols) {
     // write the buffer no in-flight launch reads: its last readers were launched before the previous
     // upload, which is when ev_xfree[b] was recorded on the compute stream
     if (c->flags_mode) {
-        // Three buffers in rotation: this one was last read two launches ago. Instead of queueing a
+        // Four buffers in rotation: this one was last read three launches ago. Instead of queueing a
         // stream wait (a stream memory operation costs ~3 us on the copy stream) the host looks at
         // done_seq itself -- in steady state the number is already there -- and then queues the copy and
         // the flag that tells the next launch its x has landed.
@@ -745,15 +834,7 @@ int hsb_sync(hsb_ctx *c) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
     c->y_busy[0] = c->y_busy[1] = false;
-    {
-        uint32_t err = 0;
-        CUDA_TRY(cudaMemcpy(&err, c->d_flags + kFlagError, 4, cudaMemcpyDeviceToHost));
-        if (err) {
-            CUDA_TRY(cudaMemset(c->d_flags + kFlagError, 0, 4));
-            return set_err(HSB_ECUDA, "a kernel gave up waiting for a flag (vector upload, result download, peer slice or accumulator reuse)");
-        }
-    }
-    return HSB_OK;
+    return check_error_flag(c);
 }
 
 int hsb_download_result_async(hsb_ctx *c, void *y_packed, unsigned num_rows) {
@@ -764,7 +845,7 @@ int hsb_download_result_async(hsb_ctx *c, void *y_packed, unsigned num_rows) {
     if (c->pending_dl.active) { int rc = finish(c); if (rc) return rc; }
     // (pageable destinations are never deferred: cudaMemcpyAsync into pageable memory blocks the calling
     // thread until the copy has run, and a deferred copy waits for a launch this thread has yet to issue)
-    uint32_t *alias = c->flags_mode && c->drain_pending ? mapped_alias(c, y_packed) : nullptr;
+    uint32_t *alias = c->flags_mode && c->drain_pending ? mapped_alias(c, y_packed, num_rows) : nullptr;
     if (alias && c->drain_begin == 0 && c->drain_end == c->rows) {
         // Deferred: the sums of the last SpMV are still in the row accumulators. The next whole-matrix
         // hsb_spmv drains them in its prologue anyway; the copy is attached to that launch (run_slot), or
@@ -784,7 +865,7 @@ int hsb_download_result(hsb_ctx *c, void *y_packed, unsigned num_rows) {
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
     c->y_busy[0] = c->y_busy[1] = false;
-    return HSB_OK;
+    return check_error_flag(c);      // a launch that gave up on a flag produced no row updates: never hand that out as y
 }
 
 int hsb_top_wrapper(int impl, const void *const matrix_hbm[HSB_NUM_HBM_CHANNELS], const void *x, void *y,
@@ -808,7 +889,11 @@ int hsb_top_wrapper(int impl, const void *const matrix_hbm[HSB_NUM_HBM_CHANNELS]
     if (!hsb::cpsr_decode(cfg, imgs, lens, nrp, num_col_partitions, row_part_id, row_part_id + 1, &rows_here,
                           num_cols, &csr, &err))
         return set_err(HSB_EINVAL, "malformed CPSR image: " + err);
-    hsb_ctx *c = hsb_create(0, impl);
+    // the calling thread's current device (cudaSetDevice), or HSB_DEVICE
+    int dev = 0;
+    if (const char *e = std::getenv("HSB_DEVICE")) dev = std::atoi(e);
+    else if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    hsb_ctx *c = hsb_create(dev, impl);
     if (!c) return HSB_ECUDA;
     int rc = hsb_upload_matrix_csr(c, csr.rows, csr.cols, csr.indptr.data(), csr.indices.data(), csr.vals.data(), 0);
     if (rc == HSB_OK) rc = hsb_upload_vector(c, x, num_cols);
@@ -971,8 +1056,32 @@ struct PeerBlob {                      // what hsb_peer_export hands to the othe
     cudaIpcMemHandle_t x, flags;
     uint64_t x_stride;
     uint32_t x_words, x_latest;
+    // contexts of ONE process (one host thread per GPU, or several contexts on one GPU) cannot open their own
+    // IPC handles: they recognise each other by pid and use the raw pointers (peer access enabled on demand)
+    uint64_t pid, raw_x, raw_flags;
+    int32_t device;
 };
 static_assert(sizeof(PeerBlob) <= HSB_PEER_BLOB_BYTES, "blob size");
+
+struct GatherBlob {                    // hsb_gather_export
+    cudaIpcMemHandle_t y, flags;
+    uint64_t pid, raw_y, raw_flags;
+    uint32_t total_rows, has_buffer;
+    int32_t device;
+};
+static_assert(sizeof(GatherBlob) <= HSB_PEER_BLOB_BYTES, "blob size");
+
+// make memory of `peer_device` (same process) addressable from the current device
+cudaError_t enable_peer(int my_device, int peer_device) {
+    if (my_device == peer_device) return cudaSuccess;
+    int can = 0;
+    cudaError_t e = cudaDeviceCanAccessPeer(&can, my_device, peer_device);
+    if (e != cudaSuccess) return e;
+    if (!can) return cudaErrorPeerAccessUnsupported;
+    e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    return e;
+}
 }  // namespace
 
 int hsb_peer_export(hsb_ctx *c, void *blob) {
@@ -985,6 +1094,8 @@ int hsb_peer_export(hsb_ctx *c, void *blob) {
     CUDA_TRY(cudaIpcGetMemHandle(&b.x, c->d_x[0]));
     CUDA_TRY(cudaIpcGetMemHandle(&b.flags, c->d_peer));
     b.x_stride = c->x_stride; b.x_words = c->x_words; b.x_latest = (uint32_t)c->x_latest;
+    b.pid = (uint64_t)getpid(); b.raw_x = (uint64_t)(uintptr_t)c->d_x[0]; b.raw_flags = (uint64_t)(uintptr_t)c->d_peer;
+    b.device = c->device;
     std::memset(blob, 0, HSB_PEER_BLOB_BYTES);
     std::memcpy(blob, &b, sizeof b);
     return HSB_OK;
@@ -997,20 +1108,125 @@ int hsb_peer_connect(hsb_ctx *c, int world, int rank, const void *blobs) {
     if (!c->flags_mode) return set_err(HSB_ESTATE, "the peer iteration needs the flag pipeline (stream memory operations)");
     CUDA_TRY(cudaSetDevice(c->device));
     { int rc = quiesce(c); if (rc) return rc; }
+    close_peers(c);                        // a repeated connect replaces the old mappings instead of leaking them
+    CUDA_TRY(cudaMemsetAsync(c->d_peer, 0, 64 * 4, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     for (int g = 0; g < world; g++) {
         PeerBlob b;
         std::memcpy(&b, (const char *)blobs + (size_t)g * HSB_PEER_BLOB_BYTES, sizeof b);
-        if (b.x_words != c->x_words || b.x_stride != c->x_stride || (int)b.x_latest != c->x_latest)
+        if (b.x_words != c->x_words || b.x_stride != c->x_stride || (int)b.x_latest != c->x_latest) {
+            close_peers(c);
             return set_err(HSB_EINVAL, "rank " + std::to_string(g) + " has a different vector layout or upload history");
+        }
         if (g == rank) { c->peer_x[g] = c->d_x[0]; c->peer_flags[g] = c->d_peer; continue; }
-        void *px = nullptr, *pf = nullptr;
-        CUDA_TRY(cudaIpcOpenMemHandle(&px, b.x, cudaIpcMemLazyEnablePeerAccess));
-        CUDA_TRY(cudaIpcOpenMemHandle(&pf, b.flags, cudaIpcMemLazyEnablePeerAccess));
-        c->peer_x[g] = (uint32_t *)px; c->peer_flags[g] = (uint32_t *)pf;
+        cudaError_t e;
+        if (b.pid == (uint64_t)getpid()) {
+            e = enable_peer(c->device, b.device);
+            c->peer_x[g] = (uint32_t *)(uintptr_t)b.raw_x; c->peer_flags[g] = (uint32_t *)(uintptr_t)b.raw_flags;
+        } else {
+            void *px = nullptr, *pf = nullptr;
+            e = cudaIpcOpenMemHandle(&px, b.x, cudaIpcMemLazyEnablePeerAccess);
+            if (e == cudaSuccess) {
+                e = cudaIpcOpenMemHandle(&pf, b.flags, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) cudaIpcCloseMemHandle(px);
+            }
+            if (e == cudaSuccess) { c->peer_x[g] = (uint32_t *)px; c->peer_flags[g] = (uint32_t *)pf; c->peer_ipc[g] = true; }
+        }
+        if (e != cudaSuccess) {
+            close_peers(c);
+            cudaGetLastError();
+            return set_err(HSB_ECUDA, "cannot map the vector buffers of rank " + std::to_string(g) + ": " + cudaGetErrorString(e));
+        }
     }
     c->peer_world = world; c->peer_rank = rank; c->peer_seq = 0;
     return HSB_OK;
 }
+
+// ---- gather of y across row-block shards: the drain's epilogue stores into the targets' buffers --------------
+int hsb_gather_export(hsb_ctx *c, uint32_t total_rows, int want_buffer, void *blob) {
+    if (!c || !blob || !total_rows) return set_err(HSB_EINVAL, "bad argument");
+    if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    { int rc = quiesce(c); if (rc) return rc; }
+    close_gather(c);
+    CUDA_TRY(cudaMalloc(&c->d_gather_flags, 64 * 4));
+    CUDA_TRY(cudaMemset(c->d_gather_flags, 0, 64 * 4));
+    CUDA_TRY(cudaMalloc(&c->d_gather_y, (want_buffer ? (size_t)total_rows : 1) * 4));
+    CUDA_TRY(cudaMemset(c->d_gather_y, 0, (want_buffer ? (size_t)total_rows : 1) * 4));
+    c->gather_total_rows = total_rows;
+    c->gather_is_target = want_buffer != 0;
+    GatherBlob b;
+    std::memset(&b, 0, sizeof b);
+    CUDA_TRY(cudaIpcGetMemHandle(&b.y, c->d_gather_y));
+    CUDA_TRY(cudaIpcGetMemHandle(&b.flags, c->d_gather_flags));
+    b.pid = (uint64_t)getpid(); b.raw_y = (uint64_t)(uintptr_t)c->d_gather_y; b.raw_flags = (uint64_t)(uintptr_t)c->d_gather_flags;
+    b.total_rows = total_rows; b.has_buffer = want_buffer ? 1u : 0u; b.device = c->device;
+    std::memset(blob, 0, HSB_PEER_BLOB_BYTES);
+    std::memcpy(blob, &b, sizeof b);
+    return HSB_OK;
+}
+
+int hsb_gather_connect(hsb_ctx *c, int world, int rank, uint32_t row_offset, const void *blobs) {
+    if (!c || !blobs || world < 1 || world > hsb::kMaxPeers || rank < 0 || rank >= world)
+        return set_err(HSB_EINVAL, "bad argument");
+    if (!c->have_matrix || !c->d_gather_flags) return set_err(HSB_ESTATE, "call hsb_gather_export first");
+    if ((uint64_t)row_offset + c->rows > c->gather_total_rows)
+        return set_err(HSB_EINVAL, "this rank's row block does not fit in the gathered vector");
+    CUDA_TRY(cudaSetDevice(c->device));
+    { int rc = quiesce(c); if (rc) return rc; }
+    hsb::GatherTargets t;
+    std::memset(&t, 0, sizeof t);
+    for (int g = 0; g < world; g++) {
+        GatherBlob b;
+        std::memcpy(&b, (const char *)blobs + (size_t)g * HSB_PEER_BLOB_BYTES, sizeof b);
+        if (b.total_rows != c->gather_total_rows) return set_err(HSB_EINVAL, "rank " + std::to_string(g) + " gathers a different row count");
+        if (!b.has_buffer) continue;                        // not a target
+        uint32_t *py = nullptr, *pf = nullptr;
+        if (g == rank) { py = c->d_gather_y; pf = c->d_gather_flags; }
+        else if (b.pid == (uint64_t)getpid()) {
+            cudaError_t e = enable_peer(c->device, b.device);
+            if (e != cudaSuccess) { cudaGetLastError(); return set_err(HSB_ECUDA, std::string("no peer access to a target rank: ") + cudaGetErrorString(e)); }
+            py = (uint32_t *)(uintptr_t)b.raw_y; pf = (uint32_t *)(uintptr_t)b.raw_flags;
+        } else {
+            void *a = nullptr, *f = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&a, b.y, cudaIpcMemLazyEnablePeerAccess);
+            if (e == cudaSuccess) { c->gather_opened[c->gather_n_opened++] = a; e = cudaIpcOpenMemHandle(&f, b.flags, cudaIpcMemLazyEnablePeerAccess); }
+            if (e == cudaSuccess) c->gather_opened[c->gather_n_opened++] = f;
+            if (e != cudaSuccess) { cudaGetLastError(); return set_err(HSB_ECUDA, std::string("cannot map the gathered vector of a target rank: ") + cudaGetErrorString(e)); }
+            py = (uint32_t *)a; pf = (uint32_t *)f;
+        }
+        t.y[t.n] = py + row_offset; t.flag[t.n] = pf + rank; t.n++;
+    }
+    t.ticket = c->d_gather_flags + 32;
+    if (!c->d_gather) CUDA_TRY(cudaMalloc(&c->d_gather, sizeof t));
+    CUDA_TRY(cudaMemcpy(c->d_gather, &t, sizeof t, cudaMemcpyHostToDevice));
+    c->gather_world = world; c->gather_rank = rank; c->gather_seq = 0;
+    return HSB_OK;
+}
+
+int hsb_gather_wait(hsb_ctx *c) {
+    if (!c) return set_err(HSB_EINVAL, "null context");
+    if (!c->d_gather || !c->gather_is_target) return set_err(HSB_ESTATE, "this rank is not a gather target");
+    CUDA_TRY(cudaSetDevice(c->device));
+    { int rc = finish(c); if (rc) return rc; }              // this rank's own block of the last SpMV
+    CUDA_TRY(hsb::launch_wait_flags(c->d_gather_flags, (uint32_t)c->gather_world, c->gather_seq, c->d_flags + kFlagError, c->stream));
+    c->launches++;
+    return HSB_OK;
+}
+
+void *hsb_device_y_gathered(hsb_ctx *c) { return c && c->gather_is_target ? c->d_gather_y : nullptr; }
+
+int hsb_download_gathered(hsb_ctx *c, void *y_packed, uint32_t total_rows) {
+    if (!c || !y_packed) return set_err(HSB_EINVAL, "null argument");
+    if (total_rows > c->gather_total_rows) return set_err(HSB_EINVAL, "more rows than the gathered vector holds");
+    int rc = hsb_gather_wait(c);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(y_packed, c->d_gather_y, (size_t)total_rows * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return check_error_flag(c);
+}
+
+int hsb_device_numa_node(int device) { return device_numa_node(device); }
 
 int hsb_axpb_to_peers(hsb_ctx *c, uint32_t alpha_word, uint32_t beta_word, uint32_t col_offset) {
     if (!c) return set_err(HSB_EINVAL, "null context");
@@ -1081,6 +1297,8 @@ int hsb_set_option(hsb_ctx *c, const char *name, int value) {
         c->xwait_once = value != 0;
     } else if (n == "host_drain") {
         c->host_drain = value != 0;
+    } else if (n == "acquire") {
+        c->acquire = value != 0;
     } else {
         return set_err(HSB_EINVAL, "unknown option: " + n);
     }

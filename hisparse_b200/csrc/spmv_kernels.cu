@@ -75,24 +75,51 @@ __device__ __forceinline__ uint2 ldg_stream64(const uint2 *p) {
 #endif
     return r;
 }
-// Bounded spin on a sequence flag another engine writes (a stream memory operation on a copy stream):
-// true once (int)(flag - val) >= 0. About a second worth of polls, then give up rather than hang the GPU.
+// Bounded spin on a sequence flag another engine writes (a stream memory operation on a copy stream, a peer
+// GPU's kernel): true once (int)(flag - val) >= 0. kFlagPolls polls of ~1 us, then give up rather than hang
+// the GPU: the caller raises the error flag and SKIPS its work, so a stale vector is never multiplied.
+#ifndef HSB_FLAG_POLLS
+#define HSB_FLAG_POLLS (8u << 20)
+#endif
+constexpr uint32_t kFlagPolls = HSB_FLAG_POLLS;
 __device__ __forceinline__ unsigned long long globaltimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ bool wait_flag_geq(const uint32_t *flag, uint32_t val) {
+// Polls are relaxed; with `acquire` the successful poll is followed by fence.acq_rel.sys, which makes it an
+// acquire of the writer's release (st.release.sys of a peer GPU's kernel, or the copy engine's flag write
+// behind its copy): everything the writer did before raising the flag is visible to what this thread -- and,
+// through the CTA's mbarrier, every thread it releases -- does afterwards.
+__device__ __forceinline__ bool wait_flag_geq(const uint32_t *flag, uint32_t val, bool acquire) {
 #pragma unroll 1
-    for (uint32_t i = 0; i < (1u << 20); i++) {
+    for (uint32_t i = 0; i < kFlagPolls; i++) {
         uint32_t v;
-        // relaxed: what is read afterwards (x through the TMA / async proxy, which does not go through L1) was
-        // written to device memory by the copy engine before the flag; an acquire here costs ~3 us per launch
         asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if ((int32_t)(v - val) >= 0) return true;
+        if ((int32_t)(v - val) >= 0) {
+            if (acquire) asm volatile("fence.acq_rel.sys;" ::: "memory");
+            return true;
+        }
         __nanosleep(i < 64 ? 100 : 1000);
     }
     return false;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Grid-wide completion of a drain with a gather epilogue: the CTA that takes the last ticket knows every
+// peer store of this drain has been issued and fenced, and raises this rank's arrival flag on every target.
+__device__ __forceinline__ void gather_publish(const GatherTargets *gt, uint32_t seq) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(gt->ticket, 1u) == gridDim.x - 1) {
+            *gt->ticket = 0u;
+            __threadfence_system();
+            for (int g = 0; g < gt->n; g++)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(gt->flag[g]), "r"(seq) : "memory");
+        }
+    }
 }
 // ---------------------------------------------------------------------------------------
 // arithmetic policies
@@ -209,11 +236,11 @@ __device__ __forceinline__ uint32_t steps_of(uint32_t cnt, uint32_t i) {
 // One warp streams tile-relative steps [ta, tb): a flat, contiguous run of (512 B values + 256 B
 // columns) steps that may start and end inside a slice. Lanes own lane streams; whenever a slice
 // (or the run) ends, the lane's partial sum is added to its row and the accumulator restarts.
-template <class A, class F>
+template <class A>
 __device__ __forceinline__ void stream_steps(const SpmvParams &p, uint64_t *bar, uint32_t parity,
                                              uint32_t cnt, uint32_t slice_begin, uint32_t n_slices,
                                              uint32_t step_begin, uint32_t ta, uint32_t tb, uint32_t first_slice,
-                                             uint32_t lane, bool first_segment, F &before_x_wait) {
+                                             uint32_t lane, bool first_segment, const volatile uint32_t *abort_flag) {
     uint32_t remaining = tb - ta;
     const size_t base = (size_t)(step_begin + ta) * kStepElems;
     const uint4 *vp = reinterpret_cast<const uint4 *>(p.vals + base) + lane;
@@ -245,10 +272,11 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, uint64_t *bar,
             if (sl + 1 + a < n_slices) row_next[a] = __ldg(rp + (1 + a) * kLanes);
     }
 
-    if (first_segment) before_x_wait();                      // the accumulator buffer is ours (see the kernel)
+    // x tile staged AND (first segment) the accumulator buffer is ours: thread 0 arrives on the barrier a
+    // second time once it has seen the guard flag, see the kernel
     mbar_wait(bar, parity);
     if (p.timeline && first_segment && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[(size_t)(p.seq & 255u) * 8 + 4] = globaltimer();
-    if (!remaining) return;
+    if (!remaining || *abort_flag) return;                  // a flag wait timed out: no row update from stale data
 
     uint32_t xs_base = smem_u32(xs);
     asm volatile("" : "+r"(xs_base));                        // keep it in a register: no per-step rematerialisation
@@ -309,6 +337,7 @@ template <class A>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const SpmvParams p) {
     unsigned char *smem_raw = reinterpret_cast<unsigned char *>(xs);
     __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t abort_flag;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t g0 = __ldg(p.cta_seg + blockIdx.x), g1 = __ldg(p.cta_seg + blockIdx.x + 1);
@@ -328,18 +357,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
 
     // The accumulator buffer of this launch was last used four launches ago and re-zeroed by the drain at
     // the end of launch seq-3. In the steady state that launch is long gone; the guard only ever spins when
-    // several small launches are resident at once.
-    auto guard = [&]() {
+    // several small launches are resident at once. ONE thread checks it (acquire), after it has issued the x
+    // copies, and only then arrives on the CTA's barrier a second time: every warp's first row update is
+    // ordered behind the barrier, hence behind the guard, and the poll overlaps the x staging.
+    auto guard = [&]() -> bool {
         if (p.sync_start) asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (p.guard_flag) {
-            if (lane == 0 && !wait_flag_geq(p.guard_flag, p.guard_val)) atomicExch(p.error_flag, 1u);
-            __syncwarp();
-        }
+        if (p.guard_flag && !wait_flag_geq(p.guard_flag, p.guard_val, true)) return false;
+        return true;
     };
 
     if (g0 < g1) {
         if (tid == 0) {
-            mbar_init(&bar, 1);
+            mbar_init(&bar, 2);                                   // arrive.expect_tx (x bytes) + arrive (guard passed)
+            abort_flag = 0u;
         }
         if (tid < kColBias) xs[tid] = 0u;                         // what padding slots multiply by
         __syncthreads();
@@ -351,9 +381,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
             const uint32_t cnt = __ldg(&sg->cnt_ge[lane]);
             // stage the x tile: the vector loader + vecbuf writer of the reference
             if (tid == 0) {
-                if (g == g0 && p.wait_x_flag)
-                    for (uint32_t i = 0; i < p.wait_x_count; i++)
-                        if (!wait_flag_geq(p.wait_x_flag + i, p.wait_x_val)) atomicExch(p.error_flag, 1u);
+                bool ok = true;
+                if (g == g0 && p.wait_x_flag) {
+                    for (uint32_t i = 0; i < p.wait_x_count; i++) ok &= wait_flag_geq(p.wait_x_flag + i, p.wait_x_val, p.acquire != 0);
+                    // the vector was written through the generic proxy (peer SM stores) or by the copy engine;
+                    // the bulk copy below reads it through the async proxy
+                    if (p.acquire) asm volatile("fence.proxy.async;" ::: "memory");
+                }
                 if (tl && blockIdx.x == 0 && g == g0) tl[1] = globaltimer();
                 fence_proxy_async();
                 const uint32_t bytes = h1.x * 4u;
@@ -368,11 +402,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
                     bulk_g2s(smem_raw + kXTileOffset + off, src + off, min(kBulkPiece, bytes - off), &bar);
                     k = k + 1 == pieces ? 0 : k + 1;
                 }
+                if (g == g0) ok &= guard();
+                if (!ok) {                                     // timed out: nobody multiplies, the host hears of it
+                    abort_flag = 1u;
+                    atomicExch(p.error_flag, 1u);
+                }
+                mbar_arrive(&bar);
             }
             // this warp's equal-cost share of the segment (host plan)
             const uint32_t ta = __ldg(&sg->warp_t[warp]), tb = __ldg(&sg->warp_t[warp + 1]);
             const uint32_t first_slice = __ldg(&sg->warp_slice[warp]);
-            stream_steps<A>(p, &bar, parity, cnt, h1.y, h1.z, h1.w, ta, tb, first_slice, lane, g == g0, guard);
+            stream_steps<A>(p, &bar, parity, cnt, h1.y, h1.z, h1.w, ta, tb, first_slice, lane, g == g0, &abort_flag);
             parity ^= 1u;
             if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * (kWarps + 2) + warp] = clock64() - t_start;
             __syncthreads();                                       // everyone is done with this x tile
@@ -386,21 +426,27 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
     if (tl && blockIdx.x == 0 && tid == 0) tl[2] = globaltimer();
     if (p.drain_acc) {
         if (p.wait_y_flag) {                                     // y is still being copied to the host
-            if (lane == 0 && !wait_flag_geq(p.wait_y_flag, p.wait_y_val)) atomicExch(p.error_flag, 1u);
+            if (lane == 0 && !wait_flag_geq(p.wait_y_flag, p.wait_y_val, false)) atomicExch(p.error_flag, 1u);
             __syncwarp();
         }
+        const GatherTargets *gt = p.gather;
+        const int n_targets = gt ? gt->n : 0;
         for (uint32_t r = p.drain_begin + blockIdx.x * kThreads + tid; r < p.drain_end; r += gridDim.x * kThreads) {
             const uint32_t v = A::drain(p.drain_acc, r);
             p.y[r] = v;
             if (p.y_host && r < p.y_host_rows) __stcs(p.y_host + r, v);        // posted write over PCIe
+            for (int g = 0; g < n_targets; g++) gt->y[g][r] = v;               // NVLink peer stores, coalesced
         }
         if (blockIdx.x == 0 && tid == 0) (void)A::drain(p.drain_acc, p.trash_row);
+        if (gt) gather_publish(gt, p.gather_seq);
     }
     // The predecessor is complete and its writes are visible: announce it -- to later launches (guard), to
     // the host (upload throttling reads the mapped copy) and to the copy streams (cuStreamWaitValue32).
-    // Relaxed stores: griddepcontrol.wait has already ordered the predecessor's writes.
+    // griddepcontrol.wait has already ordered the predecessor's writes; the device word is a release so that
+    // the guard's acquire in a later launch pairs with it formally, the host word (read for write-after-read
+    // throttling of uploads only) stays relaxed.
     if (blockIdx.x == 0 && tid == 0) {
-        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.done_dev), "r"(p.seq - 1u) : "memory");
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.done_dev), "r"(p.seq - 1u) : "memory");
         if (p.done_seq) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.done_seq), "r"(p.seq - 1u) : "memory");
         if (tl) tl[3] = globaltimer();
     }
@@ -409,10 +455,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
 }
 
 template <class A>
-__global__ void drain_kernel(void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end, uint32_t trash_row) {
-    for (uint32_t r = row_begin + blockIdx.x * blockDim.x + threadIdx.x; r < row_end; r += gridDim.x * blockDim.x)
-        y[r] = A::drain(acc, r);
+__global__ void drain_kernel(void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end, uint32_t trash_row,
+                             const GatherTargets *gt, uint32_t gather_seq) {
+    const int n_targets = gt ? gt->n : 0;
+    for (uint32_t r = row_begin + blockIdx.x * blockDim.x + threadIdx.x; r < row_end; r += gridDim.x * blockDim.x) {
+        const uint32_t v = A::drain(acc, r);
+        y[r] = v;
+        for (int g = 0; g < n_targets; g++) gt->y[g][r] = v;
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) (void)A::drain(acc, trash_row);
+    if (gt) gather_publish(gt, gather_seq);
+}
+
+// root side of the gather: later work on the stream sees the blocks of all ranks
+__global__ void wait_flags_kernel(const uint32_t *flags, uint32_t count, uint32_t val, uint32_t *error_flag) {
+    for (uint32_t i = 0; i < count; i++)
+        if (!wait_flag_geq(flags + i, val, true)) atomicExch(error_flag, 1u);
 }
 
 // The step between two SpMVs of an iterative caller (PageRank-style x <- alpha (*) A x (+) beta): final y
@@ -455,12 +513,19 @@ __global__ void axpb_peers_kernel(void *acc, uint32_t *y, const PeerTargets t, u
     }
 }
 
+int g_sm_count = 148;                 // configure_kernels() replaces it with the device's count
+
 }  // namespace
+
+cudaError_t launch_wait_flags(const uint32_t *flags, uint32_t count, uint32_t val, uint32_t *error_flag, cudaStream_t stream) {
+    wait_flags_kernel<<<1, 1, 0, stream>>>(flags, count, val, error_flag);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_axpb_peers(int arith, void *acc, uint32_t *y, const PeerTargets &t, uint32_t rows, uint32_t x_limit,
                               uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, uint32_t seq,
                               uint32_t *ticket, cudaStream_t stream) {
-    const int grid = (int)std::min<uint32_t>((std::max(rows, 1u) + 255) / 256, 148u * 4u);
+    const int grid = (int)std::min<uint32_t>((std::max(rows, 1u) + 255) / 256, (uint32_t)g_sm_count * 4u);
     if (arith == kArithFixed)
         axpb_peers_kernel<FixedArith><<<grid, 256, 0, stream>>>(acc, y, t, rows, x_limit, alpha, beta, col_offset, trash_row, seq, ticket);
     else
@@ -470,7 +535,7 @@ cudaError_t launch_axpb_peers(int arith, void *acc, uint32_t *y, const PeerTarge
 
 cudaError_t launch_axpb(int arith, void *acc, uint32_t *y, uint32_t *x_next, uint32_t rows, uint32_t x_limit,
                         uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, cudaStream_t stream) {
-    const int grid = (int)std::min<uint32_t>((std::max(rows, 1u) + 255) / 256, 148u * 8u);
+    const int grid = (int)std::min<uint32_t>((std::max(rows, 1u) + 255) / 256, (uint32_t)g_sm_count * 8u);
     if (arith == kArithFixed)
         axpb_kernel<FixedArith><<<grid, 256, 0, stream>>>(acc, y, x_next, rows, x_limit, alpha, beta, col_offset, trash_row);
     else
@@ -478,7 +543,8 @@ cudaError_t launch_axpb(int arith, void *acc, uint32_t *y, uint32_t *x_next, uin
     return cudaGetLastError();
 }
 
-cudaError_t configure_kernels() {
+cudaError_t configure_kernels(int sm_count) {
+    if (sm_count > 0) g_sm_count = sm_count;
     cudaError_t e = cudaFuncSetAttribute(spmv_tiles_kernel<FixedArith>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kSmemBytes);
     if (e != cudaSuccess) return e;
@@ -503,13 +569,13 @@ cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, uint32_t smem_
 }
 
 cudaError_t launch_drain(int arith, void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end,
-                         uint32_t trash_row, cudaStream_t stream) {
+                         uint32_t trash_row, const GatherTargets *gather, uint32_t gather_seq, cudaStream_t stream) {
     const uint32_t n = row_end > row_begin ? row_end - row_begin : 1;
-    const int grid = (int)std::min<uint32_t>((n + 255) / 256, 148u * 8u);
+    const int grid = (int)std::min<uint32_t>((n + 255) / 256, (uint32_t)g_sm_count * 8u);
     if (arith == kArithFixed)
-        drain_kernel<FixedArith><<<grid, 256, 0, stream>>>(acc, y, row_begin, row_end, trash_row);
+        drain_kernel<FixedArith><<<grid, 256, 0, stream>>>(acc, y, row_begin, row_end, trash_row, gather, gather_seq);
     else
-        drain_kernel<FloatArith><<<grid, 256, 0, stream>>>(acc, y, row_begin, row_end, trash_row);
+        drain_kernel<FloatArith><<<grid, 256, 0, stream>>>(acc, y, row_begin, row_end, trash_row, gather, gather_seq);
     return cudaGetLastError();
 }
 

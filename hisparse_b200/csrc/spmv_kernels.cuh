@@ -95,6 +95,20 @@ struct SpmvParams {
                                   // 4 CTA0 x tile staged, 5 last CTA end, 6 CTA0 matrix work done
     uint32_t *y_host;             // device alias of a mapped page-locked host buffer the drain ALSO writes (rows
     uint32_t y_host_rows;         // < y_host_rows), or null: a download without the copy engine
+    // Row-block shards on several GPUs (hsb_gather_connect): the drain ALSO stores every result word into the
+    // gathered-y buffer of the target ranks at this rank's row offset (peer pointers over NVLink) and, when the
+    // whole grid is through, raises this rank's arrival flag there -- the gather of y is the drain's epilogue.
+    const struct GatherTargets *gather;   // device-resident table, or null
+    uint32_t gather_seq;          // value the arrival flags receive: gathered drains so far, this one included
+    uint32_t acquire;             // 1: flag waits end in fence.acq_rel.sys (+ fence.proxy.async before the x TMA)
+};
+
+constexpr int kMaxPeers = 16;
+struct GatherTargets {
+    uint32_t *y[kMaxPeers];       // target g: its gathered-y buffer + this rank's first row
+    uint32_t *flag[kMaxPeers];    // target g: &arrival[this rank] in its flag array
+    uint32_t *ticket;             // this rank's completion counter (CTAs of one drain)
+    int n;                        // targets (1: gather to a root, world: all-gather)
 };
 
 enum { kArithFixed = 0, kArithFloat = 1 };
@@ -102,14 +116,16 @@ enum { kArithFixed = 0, kArithFloat = 1 };
 cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, uint32_t smem_bytes, cudaStream_t stream);
 // drain only: y[r] = clamp(acc[r]), acc[r] = 0 for r in [row_begin, row_end) and the trash slot
 cudaError_t launch_drain(int arith, void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end,
-                         uint32_t trash_row, cudaStream_t stream);
+                         uint32_t trash_row, const GatherTargets *gather, uint32_t gather_seq, cudaStream_t stream);
+// stream-ordered wait (one thread, acquire) until `count` consecutive arrival flags have reached `val`; a
+// timed-out wait raises *error_flag
+cudaError_t launch_wait_flags(const uint32_t *flags, uint32_t count, uint32_t val, uint32_t *error_flag, cudaStream_t stream);
 // y = final result of the last launch (drained from acc when acc != null); x_next[col_offset + r] = alpha (*) y[r] (+) beta
 cudaError_t launch_axpb(int arith, void *acc, uint32_t *y, uint32_t *x_next, uint32_t rows, uint32_t x_limit,
                         uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, cudaStream_t stream);
 // Multi-GPU form of launch_axpb: the slice alpha (*) y (+) beta is stored into the next x buffer of EVERY rank
 // (peer pointers over NVLink, this rank included) at col_offset, and when the whole grid has finished, `seq`
 // is written into this rank's slot of every rank's arrival-flag array -- compute and all-gather in one kernel.
-constexpr int kMaxPeers = 16;
 struct PeerTargets {
     uint32_t *x_next[kMaxPeers];   // next x buffer of rank g
     uint32_t *flag[kMaxPeers];     // &arrival[my rank] in rank g's flag array
@@ -118,7 +134,8 @@ struct PeerTargets {
 cudaError_t launch_axpb_peers(int arith, void *acc, uint32_t *y, const PeerTargets &t, uint32_t rows, uint32_t x_limit,
                               uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, uint32_t seq,
                               uint32_t *ticket, cudaStream_t stream);
-cudaError_t configure_kernels();
+// sm_count: SMs of the device (grid sizing of the element-wise kernels)
+cudaError_t configure_kernels(int sm_count);
 
 }  // namespace hsb
 #endif

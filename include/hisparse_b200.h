@@ -159,10 +159,28 @@ int hsb_vector_commit(hsb_ctx *ctx);
  * kernel has finished -- the compute step and the all-gather are one kernel -- and after
  * hsb_vector_commit the next hsb_spmv polls the arrival flags of all ranks before it stages x. No NCCL
  * call, no host synchronisation inside the iteration. */
-#define HSB_PEER_BLOB_BYTES 160
+#define HSB_PEER_BLOB_BYTES 192
 int hsb_peer_export(hsb_ctx *ctx, void *blob);
 int hsb_peer_connect(hsb_ctx *ctx, int world, int rank, const void *blobs /* world x HSB_PEER_BLOB_BYTES */);
 int hsb_axpb_to_peers(hsb_ctx *ctx, uint32_t alpha_word, uint32_t beta_word, uint32_t col_offset);
+/* Gather of y across row-block shards, fused into the result drain (the role of axis_merge +
+ * spmv_result_drain, spmv/libfpga/stream_utils.h:36-75 and spmv/spmv_result_drain.cpp:36-113, which assemble
+ * ONE y from the 16 clusters' streams): once connected, every drain of this context ALSO stores its result
+ * words into the gathered vector of each target rank at `row_offset` (peer stores over NVLink) and, when the
+ * drain's grid is through, raises this rank's arrival flag there. Every rank calls hsb_gather_export
+ * (want_buffer != 0 on the ranks that receive the whole y: one root for a gather, everybody for an
+ * all-gather), the blobs are exchanged (HSB_PEER_BLOB_BYTES each, e.g. torch.distributed.all_gather or
+ * ncclAllGather), every rank calls hsb_gather_connect. All ranks must issue the same sequence of SpMVs.
+ * hsb_gather_wait (targets only) makes later work on the context's stream wait for the blocks of ALL ranks
+ * of the last SpMV; hsb_download_gathered = wait + copy to the host. The gathered vector is overwritten by
+ * the next drain: consume it (or synchronise the ranks) before issuing further SpMVs. */
+int hsb_gather_export(hsb_ctx *ctx, uint32_t total_rows, int want_buffer, void *blob);
+int hsb_gather_connect(hsb_ctx *ctx, int world, int rank, uint32_t row_offset, const void *blobs);
+int hsb_gather_wait(hsb_ctx *ctx);
+void *hsb_device_y_gathered(hsb_ctx *ctx);
+int hsb_download_gathered(hsb_ctx *ctx, void *y_packed, uint32_t total_rows);
+/* NUMA node of the GPU (sysfs), or -1 when the platform does not say; hsb_host_alloc prefers that node */
+int hsb_device_numa_node(int device);
 /* single GPU, rows <= cols: iters x { hsb_spmv; hsb_axpb_to_vector(alpha, beta, 0); hsb_vector_commit } */
 int hsb_iterate(hsb_ctx *ctx, int iters, uint32_t alpha_word, uint32_t beta_word);
 
@@ -184,7 +202,8 @@ int hsb_time_e2e(hsb_ctx *ctx, const void *const x_host[2], void *const y_host[2
 /* Tuning / A-B switches (synchronises first). "flags": 1 = flag pipeline (default when the driver offers
  * stream memory operations), 0 = stream events between launches; "xwait_once": 1 = launches stop polling
  * the x flag once one that polled it has completed (default); "host_drain": 1 = deferred downloads into
- * page-locked memory are written by the kernel's drain itself instead of the copy engine (default). */
+ * page-locked memory are written by the kernel's drain itself instead of the copy engine (default); "acquire":
+ * 1 = the kernels' flag waits end in fence.acq_rel.sys + fence.proxy.async (default), 0 = relaxed (A/B aid). */
 int hsb_set_option(hsb_ctx *ctx, const char *name, int value);
 /* Profiling aid: SM-clock stamps of the last launch, [sm_count][34] = per warp "my slices are done",
  * then CTA "finished" (wait for the predecessor and drain included); the last word is unused. out == NULL arms (capacity != 0) or
@@ -245,10 +264,6 @@ int hsb_format_expand(const hsb_format *f, uint32_t *indptr, uint32_t *indices, 
  * {cta, tile, first step, end step} with tile-relative steps. Returns the number of records (call with
  * records == NULL to size the buffer). Every step of every tile is covered exactly once. */
 long long hsb_format_plan(const hsb_format *f, uint32_t ctas, uint32_t *records, size_t capacity_records);
-/* y = A x (fixed point) computed on the HOST by walking that plan exactly as the kernel does (segments, warp
- * shares, slice geometry from the tile tables, per-lane sums handed to slice_rows): checks the contract between
- * formatter, planner and kernel without a GPU. Test aid, not a compute path: single thread, no vectorisation. */
-int hsb_format_emulate_fixed(const hsb_format *f, uint32_t ctas, const uint32_t *x_words, uint32_t *y_words);
 void hsb_format_free(hsb_format *f);
 /* Decode reference channel images back to CSR (what hsb_upload_matrix_cpsr does first).
  * indptr: num_rows + 1 words; indices / vals: capacity words each; *nnz receives the count
