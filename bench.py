@@ -10,7 +10,13 @@ the same size is generated, seed 0xC0FFEE02), fixed-point path (ap_ufixed<32,8>)
 A STEP is one batch of `--batch` SpMVs (default 512) over the resident matrix -- the reference's
 benchmark loop (sw/benchmark.cpp:315-343) with 512 instead of 50 back-to-back runs -- so that a
 step lasts milliseconds and GPU clocks can be sampled while it runs. Successive SpMVs rotate over
-enough HBM copies of the matrix that none is still in the 126 MB L2 when it is read again.
+enough HBM copies of the matrix that none is still in the L2 (126 MB on B200, queried) when it is read again.
+
+N > 1 (torchrun): `value` stays the same workload, one C2-sized matrix per GPU (so that the N=1 line is the
+first point of the curve), and a `sharded` object is added -- BASELINE.json's multi-GPU configurations run the
+way north_star splits them: ONE matrix cut into nnz-balanced row blocks (C4, ogbl-ppa-sized, at 2 and 4 GPUs;
+the device-generated C5, 100 M x 100 M power-law, at 8), x broadcast with NCCL, y gathered ON THE DEVICE by the
+result drain's peer stores over NVLink, the gathered y checked against the oracle. See sharded_block().
 
 Metric (sw/benchmark.cpp:311-346): GOPS = 2*nnz / t ; GBPS = 8*nnz bytes / 2^30 / t.
 `value` = device-timed (CUDA events on the launching stream, inputs resident in HBM);
@@ -32,7 +38,7 @@ sys.path.insert(0, ROOT)
 
 SEED = 0xC0FFEE02
 N_NODES, NNZ_TARGET = 107614, 13_670_000
-L2_BYTES = 126 * 1024 * 1024
+L2_BYTES = 126 * 1024 * 1024     # replaced by the device's own figure (hsb_device_l2_bytes) once a GPU is open
 
 
 def load_peaks():
@@ -64,6 +70,11 @@ WORKLOAD = "c2"
 
 
 SHARD_ONE_MATRIX = False
+
+
+def workload_name(nnz):
+    """config.workload: the same string in both arms (ours / --impl reference)"""
+    return (WORKLOADS[WORKLOAD][0] % ()) + ", nnz=%d" % nnz
 
 
 def workload(rank, world=1):
@@ -175,7 +186,9 @@ def run_reference(args):
     # "all threads" and "as shipped" (1 thread) as the reference's figure
     if threads > 1 and one(2, threads) > t_single:
         threads = 1
-    per_step = max(4, min(256, int(0.5 / max(one(2, threads), 1e-6))))   # a step = ~0.5 s of CPU SpMVs (bounded sample)
+    # a step = the same batch of SpMVs as our arm when that stays within ~8 s of CPU time, else a bounded sample
+    t_one = max(one(2, threads), 1e-6)
+    per_step = args.batch if args.batch * t_one <= 8.0 else max(4, int(2.0 / t_one))
     for _ in range(args.warmup):
         one(1, threads)
     t = 0.0
@@ -187,8 +200,8 @@ def run_reference(args):
            "unit": "GOPS", "gbps": 8.0 * nnz / 2 ** 30 / sec_per_spmv, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": (WORKLOADS[WORKLOAD][0] % ()) + ", nnz=%d (fp32 compute_ref on %d host thread(s))"
-                                  % (nnz, threads), "spmv_per_step": per_step},
+           "config": {"workload": workload_name(nnz), "spmv_per_step": per_step,
+                      "arm": "fp32 compute_ref (sw/host.cpp:33-48) on %d host thread(s)" % threads},
            "cpu_baseline": {"value": gops, "unit": "GOPS", "cores": threads, "kind": kind,
                             "single_thread_value": 2.0 * nnz / t_single / 1e9,
                             "sample": "%d x %d full SpMVs of the matrix" % (args.steps, per_step)},
@@ -221,6 +234,216 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<u4", "data": (ptr, False), "version": 2}
 
 
+def _max_over_ranks(dist, dev, *vals):
+    import torch
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def _sum_over_ranks(dist, dev, *vals):
+    import torch
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t]
+
+
+def sharded_block(args, dist, rank, local, world):
+    """BASELINE.json configs[3] / configs[4] the way north_star splits them: ONE matrix, nnz-balanced contiguous
+    row blocks (hisparse_b200/sharding.py), rank g holds block g and a replica of x and produces y[block g].
+    Measured, max over ranks, device timed:
+      spmv_ms            shards resident, x resident, no exchange                       (a)
+      bcast_x_ms         one ncclBroadcast of x from rank 0, alone                      (b)
+      spmv_gather_ms     as (a) with y gathered ON THE DEVICE: every rank's result drain also stores its block
+                         into rank 0's gathered vector (peer stores over NVLink) and raises an arrival flag   (c)
+      iter_ms            ncclBroadcast(x) -> SpMV -> gather, every iteration, stream ordered (no host sync)
+      parity             the gathered y of rank 0 against the oracle                    (d)
+      strong_scaling_efficiency = t(1 GPU, whole matrix) / (N * spmv_ms)   (C4; rank 0 times the whole matrix)  (e)
+    HSB_BENCH_SHARDED=c4|c5|off overrides the choice (default: c5 at 8 GPUs, c4 below)."""
+    import torch
+    from hisparse_b200 import capi, matgen, sharding
+    from oracle import hsoracle
+    which = os.environ.get("HSB_BENCH_SHARDED") or ("c5" if world >= 8 else "c4")
+    if which == "off":
+        return None
+    dev = torch.device("cuda", local)
+    port = hsoracle.Port()
+    impl = "float_pob"
+    out = {"n_gpus": world, "impl": "fp32 (float_pob semantics: multiply then add, not fused)"}
+    t_setup = time.perf_counter()
+    ctx = capi.Context(local, impl)
+    one_gpu_ms = None
+    if which == "c4":
+        rows, cols, indptr, indices, data = matgen.rmat_csr(576289, 42_460_000, 0xC0FFEE04, symmetric=True, oversample=1.5)
+        r_all, c2, ip_all = matgen.pad_csr(rows, cols, indptr, 128, 8)
+        x = np.zeros(c2, np.float32)
+        x[:cols] = np.random.default_rng(SEED).random(cols, dtype=np.float32)
+        bounds = sharding.shard_bounds(ip_all, world)
+        sip, six, sdata = sharding.extract_shard(ip_all, indices, data, bounds[rank], bounds[rank + 1])
+        if rank == 0:
+            # the single-GPU time of the SAME matrix, for the strong-scaling figure
+            ctx.upload_matrix_csr(r_all, c2, ip_all, indices, data.view(np.uint32))
+            ctx.set_replicas(max(2, int(np.ceil(2.5 * L2_BYTES / max(ctx.stats()["format_bytes"], 1)))))
+            ctx.upload_vector(x.view(np.uint32))
+            ctx.time_spmv(args.warmup * 64, 1, kernel=False)
+            one_gpu_ms, _ = ctx.time_spmv(0, max(64, args.steps * 32), kernel=False)
+        ctx.upload_matrix_csr(bounds[rank + 1] - bounds[rank], c2, sip, six, sdata.view(np.uint32))
+        out["workload"] = ("C4: ogbl-ppa-sized symmetric R-MAT %d^2, nnz=%d, fp32, cut into %d nnz-balanced row blocks"
+                           % (r_all, int(ip_all[-1]), world))
+        nnz_total = int(ip_all[-1])
+        windows = None
+        B = 128
+    else:
+        r_shard = int(os.environ.get("HSB_BENCH_C5_ROWS", "12500000"))
+        c2 = 100_000_000
+        r_all = r_shard * world
+        bounds = [g * r_shard for g in range(world + 1)]
+        dcsr = capi.DeviceCsr.powerlaw(local, r_shard, c2, first_global_row=rank * r_shard, seed=0xC0FFEE05)
+        ctx.upload_matrix_csr_device(dcsr)
+        # parity windows: the first and the last 2^19 rows of every shard come to the host, the rest never does
+        w = min(1 << 19, r_shard)
+        windows = [(0, w) + dcsr.download_rows(0, w), (r_shard - w, r_shard) + dcsr.download_rows(r_shard - w, r_shard)]
+        nnz_shard = int(dcsr.nnz)
+        dcsr.free()
+        x = np.random.default_rng(SEED).random(c2, dtype=np.float32)
+        nnz_total = int(_sum_over_ranks(dist, dev, float(nnz_shard))[0])
+        out["workload"] = ("C5: rows [0, %d) of the 100M-column power-law matrix (alpha 2.1, mean degree 20, 80 %% of a row's "
+                           "columns within +-2^20 of the diagonal), nnz=%d, fp32, generated and formatted on the devices, "
+                           "%d row blocks of %d rows" % (r_all, nnz_total, world, r_shard))
+        B = 8
+    st = ctx.stats()
+    replicas = max(1, int(np.ceil(2.5 * L2_BYTES / max(st["format_bytes"], 1)))) if st["format_bytes"] < 4 * L2_BYTES else 1
+    ctx.set_replicas(replicas)
+    # x: on rank 0 only, then one NCCL broadcast straight into the engine's device buffer
+    xw = x.view(np.uint32)
+    ctx.upload_vector(xw if rank == 0 else np.zeros(c2, np.uint32))
+    ctx.sync()
+    xt = torch.as_tensor(_DevArray(ctx.device_x(), c2), device=dev).view(torch.int32)
+    dist.broadcast(xt, 0)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+
+    def barrier():
+        ctx.sync()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    n_timed = max(B, args.steps * B // 4)
+    # (a) resident shards, no exchange
+    ctx.time_spmv(args.warmup * B, 1, kernel=False)
+    barrier()
+    spmv_ms, _ = ctx.time_spmv(0, n_timed, kernel=False)
+    barrier()
+    # (b) the broadcast alone
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        dist.broadcast(xt, 0)
+    torch.cuda.synchronize()
+    n_b = 20
+    e0.record()
+    for _ in range(n_b):
+        dist.broadcast(xt, 0)
+    e1.record()
+    torch.cuda.synchronize()
+    bcast_ms = e0.elapsed_time(e1) / n_b
+    # gather of y: the drains store into rank 0's gathered vector from now on
+    blob = torch.from_numpy(ctx.gather_export(r_all, want_buffer=(rank == 0))).to(dev)
+    blobs = [torch.empty_like(blob) for _ in range(world)]
+    dist.all_gather(blobs, blob)
+    ctx.gather_connect(world, rank, bounds[rank], np.concatenate([b.cpu().numpy() for b in blobs]))
+    barrier()
+    # (d) parity of the gathered vector
+    ctx.spmv()
+    barrier()                                              # every rank's drain (and its peer stores) has completed
+    y_block = ctx.download_result()
+    import zlib
+    ok, parity = 1.0, ""
+    crc = float(zlib.crc32(y_block.tobytes()))
+    crcs = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(crcs, torch.tensor([crc], dtype=torch.float64, device=dev))
+    if windows is None:
+        if rank == 0:
+            yg = ctx.download_gathered().view(np.float32).astype(np.float64)
+            y64, sa = port.spmv_f64(ip_all, indices, data, x)
+            ok = float(np.all(np.abs(yg - y64) <= 1e-5 * sa + 1e-30))
+            parity = ("gathered y (%d rows on rank 0, assembled by the drains' peer stores) within 1e-5 * sum|a_i x_i| of "
+                      "the oracle's fp64 SpMV of the WHOLE matrix, all rows, checked in this run" % r_all)
+    else:
+        yb = y_block.view(np.float32).astype(np.float64)
+        for (r0, r1, wip, wix, wv) in windows:
+            y64, sa = port.spmv_f64(wip, wix, wv.view(np.float32), x)
+            ok = min(ok, float(np.all(np.abs(yb[r0:r1] - y64) <= 1e-5 * sa + 1e-30)))
+        if rank == 0:
+            yg = ctx.download_gathered()
+            for g in range(world):
+                ok = min(ok, float(float(zlib.crc32(yg[bounds[g]:bounds[g + 1]].tobytes())) == float(crcs[g][0])))
+            parity = ("every rank: first and last %d rows of its block within 1e-5 * sum|a_i x_i| of the oracle's fp64 "
+                      "SpMV; rank 0: every block of the gathered y (%d rows) bit-identical (CRC-32) to the owning rank's "
+                      "own y; checked in this run" % (windows[0][1], r_all))
+    ok = -_max_over_ranks(dist, dev, -ok)[0]
+    if ok < 1.0:
+        raise SystemExit("bench: sharded SpMV result differs from the oracle -- refusing to report a number")
+    barrier()
+    # (c) the same loop with the gather fused into the drains
+    launches0 = ctx.stats()["kernel_launches"]
+    ctx.time_spmv(B, 1, kernel=False)
+    barrier()
+    launches1 = ctx.stats()["kernel_launches"]
+    gather_ms, _ = ctx.time_spmv(0, n_timed, kernel=False)
+    barrier()
+    launches2 = ctx.stats()["kernel_launches"]
+    # iteration with a fresh x every time: ncclBroadcast(x) -> SpMV (+ gather), stream ordered on the engine's stream
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    n_it = max(8, n_timed // 4)
+    with torch.cuda.stream(ext):
+        for _ in range(3):
+            dist.broadcast(xt, 0)
+            ctx.spmv()
+        barrier()
+        e0.record(ext)
+        for _ in range(n_it):
+            dist.broadcast(xt, 0)
+            ctx.spmv()
+        ctx.sync()
+        e1.record(ext)
+    torch.cuda.synchronize()
+    iter_ms = e0.elapsed_time(e1) / n_it
+    barrier()
+    spmv_ms, gather_ms, iter_ms, bcast_ms = _max_over_ranks(dist, dev, spmv_ms, gather_ms, iter_ms, bcast_ms)
+    alg_sum, fmt_sum = _sum_over_ranks(dist, dev, float(st["algorithmic_bytes"]), float(st["format_bytes"]))
+    peak, peak_src = load_peaks()
+    gops = lambda ms: 2.0 * nnz_total / (ms / 1e3) / 1e9
+    out.update({
+        "rows": r_all, "cols": c2, "nnz": nnz_total, "row_block_bounds": bounds if world <= 16 else None,
+        "spmv_ms": spmv_ms, "gops": gops(spmv_ms), "gbps": 8.0 * nnz_total / 2 ** 30 / (spmv_ms / 1e3),
+        "spmv_gather_ms": gather_ms, "gops_with_gather": gops(gather_ms),
+        "bcast_x_ms": bcast_ms, "bcast_x_gbs": c2 * 4 / (bcast_ms / 1e3) / 1e9,
+        "iter_ms": iter_ms, "gops_bcast_every_spmv": gops(iter_ms),
+        "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+                     "achieved_per_gpu": alg_sum / world / (spmv_ms / 1e3) / 1e9,
+                     "frac": alg_sum / world / (spmv_ms / 1e3) / 1e9 / peak,
+                     "format_frac": fmt_sum / world / (spmv_ms / 1e3) / 1e9 / peak,
+                     "note": "algorithmic bytes of a shard (mean over ranks; every shard counts the whole x once) / the "
+                             "slowest rank's time per SpMV"},
+        "gpu_launches_per_spmv_with_gather": (launches2 - launches1) / float(n_timed),
+        "spmv_timed": n_timed, "l2_policy": "%d HBM replica(s) of the shard round-robin (%.0f MB each)" % (replicas, st["format_bytes"] / 1e6),
+        "parity": parity, "setup_s": setup_s,
+        "exchange": "x: ncclBroadcast from rank 0 (torch.distributed, NCCL over NVLink) into the engine's device buffer; "
+                    "y: no collective call -- the result drain at the end of every SpMV stores the rank's block into rank 0's "
+                    "gathered vector through peer pointers (CUDA IPC) and raises an arrival flag (hsb_gather_connect)",
+        "limiting_collective": ("ncclBroadcast(x): %.3f ms against %.3f ms per SpMV; the gather of y costs %.3f ms per SpMV "
+                                "(fused into the drain)" % (bcast_ms, spmv_ms, gather_ms - spmv_ms)),
+    })
+    if one_gpu_ms is not None or which == "c4":
+        t1 = _max_over_ranks(dist, dev, one_gpu_ms or 0.0)[0]
+        out["one_gpu_ms"] = t1
+        out["strong_scaling_speedup"] = t1 / spmv_ms
+        out["strong_scaling_efficiency"] = t1 / (world * spmv_ms)
+        out["strong_scaling_efficiency_with_gather"] = t1 / (world * gather_ms)
+    ctx.close()
+    return out if rank == 0 else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -234,7 +457,7 @@ def main():
     ap.add_argument("--shard-one-matrix", action="store_true",
                     help="N > 1: row-block shards of ONE matrix (strong scaling) instead of one matrix per rank")
     args = ap.parse_args()
-    global WORKLOAD, SHARD_ONE_MATRIX
+    global WORKLOAD, SHARD_ONE_MATRIX, L2_BYTES
     WORKLOAD = args.workload
     SHARD_ONE_MATRIX = args.shard_one_matrix
     if args.impl == "reference":
@@ -252,6 +475,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from hisparse_b200 import matgen
+    L2_BYTES = capi.device_l2_bytes(local) or L2_BYTES
     impl = WORKLOADS[WORKLOAD][1]
     ctx = capi.Context(local, impl)
     if WORKLOAD == "c5s":
@@ -397,6 +621,28 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s, e2e_sync_s = float(t[0]), float(t[1])
 
+    # the checker: the result words of this very run against the oracle's closed form -- on EVERY rank (each has
+    # its own matrix or its own row block)
+    from oracle import hsoracle
+    port = hsoracle.Port()
+    if impl == "fixed":
+        ok = bool(np.array_equal(y, port.spmv_q824(ip2, indices, words, xw)))
+        parity = "bit-exact vs oracle (closed form of ap_ufixed<32,8,AP_RND,AP_SAT> as written in oracle/shim/ap_fixed.h)"
+    else:
+        y64, sa = port.spmv_f64(ip2, indices, data, x)
+        ok = bool(np.all(np.abs(y.view(np.float32).astype(np.float64) - y64) <= 1e-5 * sa + 1e-30))
+        parity = "within 1e-5 * sum|a_i x_i| of the oracle's fp64 SpMV"
+    parity += " checked in this run" + (" on every rank" if world > 1 else "")
+    if dist is not None:
+        ok = _max_over_ranks(dist, "cuda:%d" % local, 0.0 if ok else 1.0)[0] == 0.0
+    if not ok:
+        raise SystemExit("bench: GPU result differs from the oracle -- refusing to report a number")
+    ctx.close()
+    ctx = None
+    sharded = None
+    if world > 1 and WORKLOAD == "c2" and not SHARD_ONE_MATRIX:
+        sharded = sharded_block(args, dist, rank, local, world)
+
     if rank == 0:
         peak, peak_src = load_peaks()
         sec_per_spmv = total_ms / 1e3 / (args.steps * B)
@@ -415,8 +661,7 @@ def main():
             "scaling": "strong" if (SHARD_ONE_MATRIX and world > 1) else "weak", "vs_baseline": None,
             "dtype": "u32 Q8.24 (ap_ufixed<32,8,AP_RND,AP_SAT>), 64-bit accumulate" if impl == "fixed" else "f32",
             "data": "synthetic",
-            "config": {"workload": (WORKLOADS[WORKLOAD][0] % ()) + ", nnz=%d per GPU" % nnz,
-                       "spmv_per_step": B, "l2_policy": "inputs larger than L2: %d HBM replicas of the matrix "
+            "config": {"workload": workload_name(nnz), "spmv_per_step": B, "l2_policy": "inputs larger than L2: %d HBM replicas of the matrix "
                        "(%.0f MB each) used round-robin" % (replicas, st["format_bytes"] / 1e6),
                        "sharding": (("nnz-balanced row-block shards of ONE matrix" if SHARD_ONE_MATRIX else
                                      "one matrix of the workload's size per GPU") +
@@ -448,22 +693,14 @@ def main():
             "clocks": sampler.summary(),
             "preprocess_s": st["preprocess_seconds"],
         }
+        out["config"]["parity"] = parity
+        if sharded is not None:
+            out["sharded"] = sharded
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(r2, c2, ip2, indices, data, x, nnz)
-            # the checker: the result words of this very run against the oracle's closed form
-            from oracle import hsoracle
-            port = hsoracle.Port()
-            if impl == "fixed":
-                ok = np.array_equal(y, port.spmv_q824(ip2, indices, words, xw))
-                out["config"]["parity"] = "bit-exact vs oracle checked in this run"
-            else:
-                y64, sa = port.spmv_f64(ip2, indices, data, x)
-                ok = bool(np.all(np.abs(y.view(np.float32).astype(np.float64) - y64) <= 1e-5 * sa + 1e-30))
-                out["config"]["parity"] = "within 1e-5 * sum|a_i x_i| of fp64 checked in this run"
-            if not ok:
-                raise SystemExit("bench: GPU result differs from the oracle -- refusing to report a number")
         print(json.dumps(out))
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if dist is not None:
         dist.destroy_process_group()
 

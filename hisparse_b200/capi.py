@@ -121,6 +121,8 @@ def lib():
     L.hsb_device_y_gathered.restype = vp
     L.hsb_download_gathered.argtypes = [vp, vp, u32]
     L.hsb_device_numa_node.argtypes = [C.c_int]
+    L.hsb_device_l2_bytes.argtypes = [C.c_int]
+    L.hsb_device_l2_bytes.restype = sz
     L.hsb_debug_trace.argtypes = [vp, vp, sz]
     L.hsb_debug_timeline.argtypes = [vp, vp, sz]
     L.hsb_debug_plan.argtypes = [vp, vp, vp, sz]
@@ -182,6 +184,10 @@ def device_count():
     return lib().hsb_device_count()
 
 
+def device_l2_bytes(device=0):
+    return int(lib().hsb_device_l2_bytes(device))
+
+
 def _images_args(images):
     imgs = [np.ascontiguousarray(im, dtype=np.uint32) for im in images]
     arr = (C.c_void_p * 16)(*[im.ctypes.data for im in imgs])
@@ -237,6 +243,24 @@ class DeviceCsr:
         if rc != 0:
             raise HsbError("hsb_device_csr_download: " + lib().hsb_synth_last_error().decode())
         return indptr, indices[:self.nnz], vals[:self.nnz]
+
+    def download_rows(self, r0, r1):
+        """CSR of rows [r0, r1) only (indptr rebased to 0): a window of a shard too big to bring to the host whole"""
+        assert 0 <= r0 <= r1 <= self.rows
+        win = DeviceCsrStruct()
+        win.rows, win.cols, win.device = r1 - r0, self.cols, self.st.device
+        win.d_indptr = self.st.d_indptr + 4 * r0
+        indptr = np.empty(r1 - r0 + 1, np.uint32)
+        if lib().hsb_device_csr_download(C.byref(win), _ptr(indptr), None, None) != 0:
+            raise HsbError("hsb_device_csr_download: " + lib().hsb_synth_last_error().decode())
+        e0, e1 = int(indptr[0]), int(indptr[-1])
+        win.nnz = e1 - e0
+        win.d_indices, win.d_vals = self.st.d_indices + 4 * e0, self.st.d_vals + 4 * e0
+        indices = np.empty(max(win.nnz, 1), np.uint32)
+        vals = np.empty(max(win.nnz, 1), np.uint32)
+        if lib().hsb_device_csr_download(C.byref(win), None, _ptr(indices), _ptr(vals)) != 0:
+            raise HsbError("hsb_device_csr_download: " + lib().hsb_synth_last_error().decode())
+        return (indptr - np.uint32(e0)).astype(np.uint32), indices[:win.nnz], vals[:win.nnz]
 
     def free(self):
         if self.st.d_indptr:

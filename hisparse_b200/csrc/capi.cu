@@ -1228,6 +1228,12 @@ int hsb_download_gathered(hsb_ctx *c, void *y_packed, uint32_t total_rows) {
 
 int hsb_device_numa_node(int device) { return device_numa_node(device); }
 
+size_t hsb_device_l2_bytes(int device) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, device) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return (size_t)v;
+}
+
 int hsb_axpb_to_peers(hsb_ctx *c, uint32_t alpha_word, uint32_t beta_word, uint32_t col_offset) {
     if (!c) return set_err(HSB_EINVAL, "null context");
     if (!c->have_matrix || c->peer_world < 1) return set_err(HSB_ESTATE, "call hsb_peer_connect first");

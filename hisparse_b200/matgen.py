@@ -13,7 +13,13 @@ import numpy as np
 
 def _finish(rows, cols, r, c, rng, values):
     key = r.astype(np.uint64) * np.uint64(cols) + c.astype(np.uint64)
-    key = np.unique(key)
+    # sorted distinct keys; (numpy 2.3's np.unique takes a minute for 6e7 64-bit keys, sort + mask a second)
+    key.sort()
+    if key.size:
+        keep = np.empty(key.size, bool)
+        keep[0] = True
+        np.not_equal(key[1:], key[:-1], out=keep[1:])
+        key = key[keep]
     r = (key // np.uint64(cols)).astype(np.uint32)
     c = (key % np.uint64(cols)).astype(np.uint32)
     indptr = np.zeros(rows + 1, np.uint32)

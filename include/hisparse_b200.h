@@ -181,6 +181,8 @@ void *hsb_device_y_gathered(hsb_ctx *ctx);
 int hsb_download_gathered(hsb_ctx *ctx, void *y_packed, uint32_t total_rows);
 /* NUMA node of the GPU (sysfs), or -1 when the platform does not say; hsb_host_alloc prefers that node */
 int hsb_device_numa_node(int device);
+/* L2 cache size of the device in bytes (0 on error): what a timed loop's working set has to exceed */
+size_t hsb_device_l2_bytes(int device);
 /* single GPU, rows <= cols: iters x { hsb_spmv; hsb_axpb_to_vector(alpha, beta, 0); hsb_vector_commit } */
 int hsb_iterate(hsb_ctx *ctx, int iters, uint32_t alpha_word, uint32_t beta_word);
 

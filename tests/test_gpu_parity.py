@@ -638,3 +638,100 @@ def test_cpp_benchmark_driver(gpu):
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "GOPS }" in r.stdout and "with host buffers" in r.stdout and "===== Benchmark Finished =====" in r.stdout
+
+
+# ------------------------------------------------------------------------------------------
+# row-block shards + gather of y fused into the result drain (hsb_gather_*), on one device:
+# the contexts of one process reach each other's buffers through plain pointers, the kernels,
+# the arrival flags and the bookkeeping are the ones the multi-GPU runs use (bench.py `sharded`)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world,all_targets", [(2, False), (3, True)])
+def test_sharded_spmv_gather_of_y(gpu, port, world, all_targets):
+    from hisparse_b200 import sharding
+    rows, cols, indptr, indices, data = matgen.rmat_csr(30000, 900000, 77)
+    data = (data * np.float32(0.05)).astype(np.float32)
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
+    words = port.quantize(data)
+    rng = np.random.default_rng(5)
+    xs = [port.quantize(rng.random(c2, dtype=np.float32)) for _ in range(3)]
+    bounds = sharding.shard_bounds(ip2, world)
+    ctxs = []
+    for g in range(world):
+        sip, six, sw = sharding.extract_shard(ip2, indices, words, bounds[g], bounds[g + 1])
+        c = capi.Context(0, capi.IMPL_FIXED)
+        c.upload_matrix_csr(bounds[g + 1] - bounds[g], c2, sip, six, sw)
+        c.upload_vector(xs[0])
+        ctxs.append(c)
+    blobs = np.concatenate([c.gather_export(r2, want_buffer=(all_targets or g == 0)) for g, c in enumerate(ctxs)])
+    for g, c in enumerate(ctxs):
+        c.gather_connect(world, g, bounds[g], blobs)
+    targets = ctxs if all_targets else ctxs[:1]
+    # one SpMV, drained (and gathered) by hsb_sync
+    for c in ctxs:
+        c.spmv()
+    for c in ctxs:
+        c.sync()
+    want = port.spmv_q824(ip2, indices, words, xs[0])
+    for t in targets:
+        assert np.array_equal(t.download_gathered(), want)
+    # back-to-back SpMVs: the first is drained by the END of the second launch, the second by hsb_sync;
+    # the gathered vector holds the last one
+    for k in (1, 2):
+        for c in ctxs:
+            c.upload_vector(xs[k])
+            c.spmv()
+    for c in ctxs:
+        c.sync()
+    want = port.spmv_q824(ip2, indices, words, xs[2])
+    for t in targets:
+        assert np.array_equal(t.download_gathered(), want)
+    # every rank still has its own block
+    for g, c in enumerate(ctxs):
+        assert np.array_equal(c.download_result(), want[bounds[g]:bounds[g + 1]])
+    if not all_targets:
+        with pytest.raises(capi.HsbError):
+            ctxs[1].download_gathered()
+    for c in ctxs:
+        c.close()
+
+
+# ------------------------------------------------------------------------------------------
+# full BASELINE sizes of the float configurations
+# ------------------------------------------------------------------------------------------
+def test_float_ogbl_ppa_size(gpu, port):
+    """config C4 stand-in at full size (576,289^2, ~42 M non-zeros, 14 column tiles), fp32"""
+    rows, cols, indptr, indices, data = matgen.rmat_csr(576289, 42_460_000, 0xC0FFEE04, symmetric=True, oversample=1.5)
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
+    x = np.zeros(c2, np.float32)
+    x[:cols] = np.random.default_rng(4).random(cols, dtype=np.float32)
+    ctx = capi.Context(0, "float_pob")
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, data)
+    ctx.upload_vector(x)
+    ctx.spmv()
+    y = ctx.download_result()
+    assert ctx.stats()["nnz"] == int(ip2[-1]) and ctx.stats()["n_col_tiles"] > 8
+    check_float(y, port, ip2, indices, data, x)
+    # linearity in x (up to rounding): A(2x) = 2 A x exactly in binary floating point
+    ctx.upload_vector((2 * x).astype(np.float32))
+    ctx.spmv()
+    y2 = ctx.download_result().view(np.float32).astype(np.float64)
+    _, sa = port.spmv_f64(ip2, indices, data, x)
+    assert np.all(np.abs(y2 - 2 * y.view(np.float32).astype(np.float64)) <= 4 * TOL * sa + 1e-30)
+    ctx.close()
+
+
+@pytest.mark.parametrize("impl", ["float_pob", "float_stall"])
+def test_float_transformer_50_percent(gpu, port, impl):
+    """config C3 at the dense end of the series: 512 x 33,288, 50 % Bernoulli mask, N(0, 0.05^2) values, x in (-1, 1)"""
+    rows, cols, indptr, indices, data = matgen.bernoulli_csr(512, 33288, 0.5, 0xC0FFEE03)
+    IF = 8 if impl == "float_stall" else 1
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128 * IF, 8)
+    x = (np.random.default_rng(2).random(c2, dtype=np.float32) * 2 - 1).astype(np.float32)
+    ctx = capi.Context(0, impl)
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, data)
+    ctx.upload_vector(x)
+    ctx.spmv()
+    y = ctx.download_result()
+    ctx.close()
+    assert int(ip2[-1]) > 8_000_000
+    check_float(y, port, ip2, indices, data, x)

@@ -90,3 +90,33 @@ def test_hypersparse_shard_parity(gpu, port, impl, rpp):
         assert np.all(np.abs(y.view(np.float32).astype(np.float64) - y64) <= TOL * sa + 1e-30)
     ctx.close()
     m.free()
+
+
+@pytest.mark.parametrize("impl", ["fixed", "float_pob"])
+def test_hypersparse_million_row_shard(gpu, port, impl):
+    """A 2^20-row block of the C5 matrix itself (100 M columns, 3052 column tiles, ~20 M non-zeros, generated and
+    formatted on the device): every row against the oracle -- fixed point bit for bit, fp32 within 1e-5 norm-wise."""
+    rows, cols = 1 << 20, 100_000_000
+    fixed = impl == "fixed"
+    m = capi.DeviceCsr.powerlaw(0, rows, cols, first_global_row=37_500_000, seed=0xC0FFEE05, q824=fixed,
+                                value_scale=0.05 if fixed else 1.0)
+    ip, ix, vv = m.download()
+    # a window fetched on its own is the same piece of the matrix
+    wip, wix, wv = m.download_rows(1000, 5000)
+    assert np.array_equal(wip, ip[1000:5001] - ip[1000]) and np.array_equal(wix, ix[ip[1000]:ip[5000]])
+    assert np.array_equal(wv, vv[ip[1000]:ip[5000]])
+    ctx = capi.Context(0, impl)
+    ctx.upload_matrix_csr_device(m)
+    m.free()
+    xf = np.random.default_rng(9).random(cols, dtype=np.float32)
+    xw = matgen.quantize_q824(xf) if fixed else xf.view(np.uint32)
+    ctx.upload_vector(xw)
+    ctx.spmv()
+    y = ctx.download_result()
+    assert ctx.stats()["n_col_tiles"] >= 3052
+    if fixed:
+        assert np.array_equal(y, port.spmv_q824(ip, ix, vv, xw))
+    else:
+        y64, sa = port.spmv_f64(ip, ix, vv.view(np.float32), xf)
+        assert np.all(np.abs(y.view(np.float32).astype(np.float64) - y64) <= TOL * sa + 1e-30)
+    ctx.close()
