@@ -32,7 +32,8 @@ thread_local std::string g_err;
 // destinations of the drain's posted writes -- memory pinned by somebody else (torch, cudaHostRegister) can be
 // unpinned behind our back and takes the copy-engine path.
 std::mutex g_host_mu;
-std::map<uintptr_t, size_t> g_host_allocs;
+struct HostAlloc { size_t bytes; uintptr_t dev; };      // dev: device alias of the base (resolved once, at allocation)
+std::map<uintptr_t, HostAlloc> g_host_allocs;
 
 int set_err(int code, const std::string &m) { g_err = m; return code; }
 
@@ -362,16 +363,12 @@ struct PreferDeviceNode {
 uint32_t *mapped_alias(hsb_ctx *c, const void *host, size_t n_words) {
     (void)c;
     const uintptr_t h = (uintptr_t)host;
-    {
-        std::lock_guard<std::mutex> lk(g_host_mu);
-        auto it = g_host_allocs.upper_bound(h);
-        if (it == g_host_allocs.begin()) return nullptr;
-        --it;
-        if (h + n_words * 4 > it->first + it->second) return nullptr;
-    }
-    void *dev = nullptr;
-    if (cudaHostGetDevicePointer(&dev, const_cast<void *>(host), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return (uint32_t *)dev;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    auto it = g_host_allocs.upper_bound(h);
+    if (it == g_host_allocs.begin()) return nullptr;
+    --it;
+    if (!it->second.dev || h + n_words * 4 > it->first + it->second.bytes) return nullptr;
+    return (uint32_t *)(it->second.dev + (h - it->first));
 }
 
 // a kernel gave up waiting for a flag: report it once (the launch skipped its row updates, y is incomplete)
@@ -640,8 +637,10 @@ void *hsb_host_alloc(size_t bytes) {
         PreferDeviceNode numa;
         if (cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     }
+    void *dev = nullptr;
+    if (cudaHostGetDevicePointer(&dev, p, 0) != cudaSuccess) { cudaGetLastError(); dev = nullptr; }
     std::lock_guard<std::mutex> lk(g_host_mu);
-    g_host_allocs[(uintptr_t)p] = bytes;
+    g_host_allocs[(uintptr_t)p] = HostAlloc{bytes, (uintptr_t)dev};
     return p;
 }
 void hsb_host_free(void *p) {

@@ -87,22 +87,38 @@ __device__ __forceinline__ unsigned long long globaltimer() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// Polls are relaxed; with `acquire` the successful poll is followed by fence.acq_rel.sys, which makes it an
-// acquire of the writer's release (st.release.sys of a peer GPU's kernel, or the copy engine's flag write
-// behind its copy): everything the writer did before raising the flag is visible to what this thread -- and,
-// through the CTA's mbarrier, every thread it releases -- does afterwards.
-__device__ __forceinline__ bool wait_flag_geq(const uint32_t *flag, uint32_t val, bool acquire) {
+// kAcqNone: relaxed polls. kAcqSys / kAcqGpu: every poll is an acquire load at that scope, so the successful one
+// synchronises with the writer's release (st.release.sys of a peer GPU's kernel, the copy engine's flag write
+// behind its copy, st.release.gpu of an earlier launch): everything the writer did before raising the flag is
+// visible to what this thread -- and, through the CTA's mbarrier, every thread it releases -- does afterwards.
+// (An acquire LOAD, not a relaxed load followed by fence.acq_rel.sys: the fence also has to wait until this SM's
+// own outstanding system-scope writes -- the previous drain's posted PCIe writes among them -- have been
+// acknowledged, which cost 1.7 us per launch device-resident and 9 us with host buffers; HSB_ACQ_FENCE=1 builds
+// that variant for A/B measurements.)
+enum { kAcqNone = 0, kAcqSys = 1, kAcqGpu = 2 };
+#ifndef HSB_ACQ_FENCE
+#define HSB_ACQ_FENCE 0
+#endif
+template <int kAcq>
+__device__ __forceinline__ bool wait_flag_geq(const uint32_t *flag, uint32_t val) {
 #pragma unroll 1
     for (uint32_t i = 0; i < kFlagPolls; i++) {
         uint32_t v;
-        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (kAcq == kAcqNone || HSB_ACQ_FENCE) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        else if (kAcq == kAcqSys) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if ((int32_t)(v - val) >= 0) {
-            if (acquire) asm volatile("fence.acq_rel.sys;" ::: "memory");
+#if HSB_ACQ_FENCE
+            if (kAcq != kAcqNone) asm volatile("fence.acq_rel.sys;" ::: "memory");
+#endif
             return true;
         }
         __nanosleep(i < 64 ? 100 : 1000);
     }
     return false;
+}
+__device__ __forceinline__ bool wait_flag_geq(const uint32_t *flag, uint32_t val, bool acquire) {
+    return acquire ? wait_flag_geq<kAcqSys>(flag, val) : wait_flag_geq<kAcqNone>(flag, val);
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -362,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
     // ordered behind the barrier, hence behind the guard, and the poll overlaps the x staging.
     auto guard = [&]() -> bool {
         if (p.sync_start) asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (p.guard_flag && !wait_flag_geq(p.guard_flag, p.guard_val, true)) return false;
+        if (p.guard_flag && !(p.acquire ? wait_flag_geq<kAcqGpu>(p.guard_flag, p.guard_val) : wait_flag_geq<kAcqNone>(p.guard_flag, p.guard_val))) return false;
         return true;
     };
 
@@ -386,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
                     for (uint32_t i = 0; i < p.wait_x_count; i++) ok &= wait_flag_geq(p.wait_x_flag + i, p.wait_x_val, p.acquire != 0);
                     // the vector was written through the generic proxy (peer SM stores) or by the copy engine;
                     // the bulk copy below reads it through the async proxy
-                    if (p.acquire) asm volatile("fence.proxy.async;" ::: "memory");
+                    if (p.acquire) asm volatile("fence.proxy.async.global;" ::: "memory");
                 }
                 if (tl && blockIdx.x == 0 && g == g0) tl[1] = globaltimer();
                 fence_proxy_async();
