@@ -170,7 +170,7 @@ def _reference_timers(r2, c2, ip2, indices, data, x):
     return "port", (lambda n, threads: port.time_spmv_f32(ip2, indices, data, x, n))
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """The reference's own CPU implementation of the path, on all the host threads it can use."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -206,7 +206,7 @@ def run_reference(args):
                             "single_thread_value": 2.0 * nnz / t_single / 1e9,
                             "sample": "%d x %d full SpMVs of the matrix" % (args.steps, per_step)},
            "e2e": {"value": gops, "unit": "GOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 def cpu_baseline(r2, c2, ip2, indices, data, x, nnz):
@@ -460,8 +460,18 @@ def main():
     global WORKLOAD, SHARD_ONE_MATRIX, L2_BYTES
     WORKLOAD = args.workload
     SHARD_ONE_MATRIX = args.shard_one_matrix
+    # stdout carries exactly ONE line, the JSON: whatever libraries print there (NCCL's version banner, ...) goes
+    # to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     from hisparse_b200 import capi
     rank = int(os.environ.get("RANK", "0"))
@@ -698,7 +708,7 @@ def main():
             out["sharded"] = sharded
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(r2, c2, ip2, indices, data, x, nnz)
-        print(json.dumps(out))
+        emit(out)
     if ctx is not None:
         ctx.close()
     if dist is not None:
