@@ -87,3 +87,19 @@ def test_cpp_npz_loader(host_bins, tmp_path):
         assert (int(out[0]), int(out[1]), int(out[2])) == (rows, cols, indices.size)
         assert abs(float(out[3]) - float(data.astype(np.float64).sum())) < 1e-2
         assert int(out[4]) == int(indices.astype(np.uint64).sum()) and int(out[5]) == int(indptr.astype(np.uint64).sum())
+
+
+def test_csim_harness_binaries_call_the_library():
+    """oracle/_ref/csim_gpu_*: the unmodified reference harness whose top_wrapper is ours. Without a GPU the
+    call must fail loudly (no CPU fallback behind the drop-in symbol)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "csim_gpu_fixed")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/csim_gpu_fixed not built")
+    syms = subprocess.run(["nm", "-u", exe], capture_output=True, text=True, check=True).stdout
+    assert "hsb_top_wrapper" in syms
+    from hisparse_b200 import capi
+    if capi.device_count() == 0:
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert r.returncode != 0 and "top_wrapper on the GPU failed" in r.stderr
