@@ -659,10 +659,15 @@ def main():
         gops = 2.0 * nnz_all / sec_per_spmv / 1e9
         alg = st["algorithmic_bytes"]
         achieved = alg / (kernel_ms / 1e3) / 1e9
-        traffic = None
+        # DRAM bytes per launch from an ncu capture -- quoted only when that capture was taken on THIS build of the
+        # library (profiles/traffic.json carries the SHA-256 of the profiled library's sources; tools/ncu_traffic.py writes it)
+        traffic, traffic_note = None, "no ncu capture of this build (profiles/traffic.json was taken on other library sources)"
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp) and WORKLOAD == "c2" and impl == "fixed":
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            if tj.get("source_sha256") == capi.source_hash():
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_note = {k: tj[k] for k in ("source", "range", "isolated_launch_us") if k in tj}
         out = {
             "metric": "SpMV GOPS (2*nnz/t, sw/benchmark.cpp:312-346)", "value": gops, "unit": "GOPS",
             "gbps": 8.0 * nnz_all / 2 ** 30 / sec_per_spmv,
@@ -679,7 +684,7 @@ def main():
                        if world > 1 else "single GPU",
                        "tile_cols": st["tile_cols"], "col_tiles": st["n_col_tiles"], "grid": st["grid"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "spmv_tiles_kernel<%s>" % ("FixedArith" if impl == "fixed" else "FloatArith"),
+                         "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "kernel": "spmv_tiles_kernel<%s>" % ("FixedArith" if impl == "fixed" else "FloatArith"),
                          "kernel_ms": kernel_ms, "kernel_ms_isolated": kernel_ms_isolated,
                          "algorithmic_bytes_per_launch": alg,
                          "format_bytes_per_launch": st["format_bytes"],

@@ -36,7 +36,7 @@ class Stats(C.Structure):
                 ("n_col_tiles", C.c_uint32), ("tile_cols", C.c_uint32), ("n_slices", C.c_uint64),
                 ("n_streams", C.c_uint64), ("n_elems", C.c_uint64), ("format_bytes", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("sm_count", C.c_uint32), ("grid", C.c_uint32),
-                ("replicas", C.c_uint32), ("preprocess_seconds", C.c_double)]
+                ("replicas", C.c_uint32), ("layout", C.c_uint32), ("preprocess_seconds", C.c_double)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -54,6 +54,19 @@ def build(force=False):
         args.insert(1, "-B")
     subprocess.run(args, check=True, stdout=subprocess.DEVNULL)
     return LIB_PATH
+
+
+def source_hash():
+    """SHA-256 over the sources libhisparse_b200.so is built from (csrc/ and the public header): identifies a
+    build across recompilations; profiles/traffic.json is keyed by it."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(HERE, "csrc", "*"))) + [HEADER]:
+        if os.path.isfile(f):
+            h.update(os.path.basename(f).encode())
+            h.update(open(f, "rb").read())
+    return h.hexdigest()
 
 
 def declared_symbols():
@@ -124,6 +137,7 @@ def lib():
     L.hsb_device_l2_bytes.argtypes = [C.c_int]
     L.hsb_device_l2_bytes.restype = sz
     L.hsb_debug_trace.argtypes = [vp, vp, sz]
+    L.hsb_debug_profiler.argtypes = [vp, C.c_int]
     L.hsb_debug_timeline.argtypes = [vp, vp, sz]
     L.hsb_debug_plan.argtypes = [vp, vp, vp, sz]
     L.hsb_format_build.argtypes = [u32, u32, vp, vp, vp, u32, u32]
@@ -426,6 +440,9 @@ class Context:
         if rc < 0:
             _check(rc)
         return rc, out.reshape(256, 8)
+
+    def profiler(self, on):
+        _check(lib().hsb_debug_profiler(self.h, 1 if on else 0))
 
     def plan(self):
         n = self.stats()["sm_count"]

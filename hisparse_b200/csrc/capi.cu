@@ -4,6 +4,7 @@
 
 #include <cuda.h>            // types of the stream memory operations only: the entry points are resolved at run time
 #include <cuda_runtime.h>
+#include <cuda_profiler_api.h>
 
 #include <algorithm>
 #include <atomic>
@@ -248,13 +249,13 @@ int install_matrix(hsb_ctx *c, const hsb::TiledMatrix &M, const DeviceMatrix &d,
     c->n_col_tiles = M.n_col_tiles; c->tile_cols = M.tile_cols;
     c->n_slices = n_slices; c->n_streams = M.n_streams; c->n_elems = n_elems;
     c->sz_vals = n_elems * 4; c->sz_cols = n_elems * 2;
-    c->sz_rows = n_slices * hsb::kLanes * 4;
+    c->sz_rows = M.narrow ? 0 : n_slices * hsb::kLanes * 4;      // narrow layout: the row ids are in the stream
     c->format_bytes = c->sz_vals + c->sz_cols + c->sz_rows;
     c->part_slice_begin = M.part_slice_begin;
     c->meta = hsb::TiledMatrix();
     c->meta.rows = M.rows; c->meta.cols = M.cols; c->meta.nnz = M.nnz; c->meta.rows_per_part = M.rows_per_part;
     c->meta.n_row_parts = M.n_row_parts; c->meta.n_col_tiles = M.n_col_tiles; c->meta.tile_cols = M.tile_cols;
-    c->meta.n_streams = M.n_streams; c->meta.slices = M.slices; c->meta.tiles = M.tiles;
+    c->meta.n_streams = M.n_streams; c->meta.slices = M.slices; c->meta.tiles = M.tiles; c->meta.narrow = M.narrow;
     c->meta.part_slice_begin = M.part_slice_begin;
     c->mats.push_back(d);
     // cost-balanced work plans for the whole-matrix launch and for each row partition
@@ -468,6 +469,7 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
     p.acc = c->d_acc[c->acc_cur];
     p.drain_acc = c->drain_pending ? c->d_acc[(c->acc_cur + c->acc_bufs - 1) % c->acc_bufs] : nullptr;
     p.acquire = c->acquire ? 1u : 0u;
+    p.narrow = c->meta.narrow ? 1u : 0u;
     if (c->d_gather && c->drain_pending) { p.gather = c->d_gather; p.gather_seq = ++c->gather_seq; }
     p.drain_begin = c->drain_begin; p.drain_end = c->drain_end;
     p.trash_row = c->rows;
@@ -703,18 +705,19 @@ int hsb_upload_matrix_csr_gpu(hsb_ctx *c, uint32_t rows, uint32_t cols, const ui
     if (rows && indptr[0] != 0) return set_err(HSB_EINVAL, "malformed CSR: indptr[0] must be 0");
     CUDA_TRY(cudaSetDevice(c->device));
     const uint64_t nnz = rows ? indptr[rows] : 0;
-    uint32_t *d_ip = nullptr, *d_ix = nullptr, *d_v = nullptr;
-    CUDA_TRY(cudaMalloc(&d_ip, ((size_t)rows + 1) * 4));
-    CUDA_TRY(cudaMalloc(&d_ix, std::max<uint64_t>(nnz, 1) * 4));
-    CUDA_TRY(cudaMalloc(&d_v, std::max<uint64_t>(nnz, 1) * 4));
-    CUDA_TRY(cudaMemcpyAsync(d_ip, indptr, ((size_t)rows + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    struct Tmp {                                           // freed on every path out, the error returns included
+        uint32_t *ip = nullptr, *ix = nullptr, *v = nullptr;
+        ~Tmp() { cudaFree(ip); cudaFree(ix); cudaFree(v); }
+    } t;
+    CUDA_TRY(cudaMalloc(&t.ip, ((size_t)rows + 1) * 4));
+    CUDA_TRY(cudaMalloc(&t.ix, std::max<uint64_t>(nnz, 1) * 4));
+    CUDA_TRY(cudaMalloc(&t.v, std::max<uint64_t>(nnz, 1) * 4));
+    CUDA_TRY(cudaMemcpyAsync(t.ip, indptr, ((size_t)rows + 1) * 4, cudaMemcpyHostToDevice, c->stream));
     if (nnz) {
-        CUDA_TRY(cudaMemcpyAsync(d_ix, indices, nnz * 4, cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(d_v, vals, nnz * 4, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(t.ix, indices, nnz * 4, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(t.v, vals, nnz * 4, cudaMemcpyHostToDevice, c->stream));
     }
-    int rc = hsb_upload_matrix_csr_device(c, rows, cols, nnz, d_ip, d_ix, d_v, rows_per_partition);
-    cudaFree(d_ip); cudaFree(d_ix); cudaFree(d_v);
-    return rc;
+    return hsb_upload_matrix_csr_device(c, rows, cols, nnz, t.ip, t.ix, t.v, rows_per_partition);
 }
 
 int hsb_upload_matrix_cpsr(hsb_ctx *c, const void *const ch[HSB_NUM_HBM_CHANNELS],
@@ -915,6 +918,7 @@ int hsb_get_stats(hsb_ctx *c, hsb_stats *out) {
     out->algorithmic_bytes = 8ull * c->nnz + 4ull * ((uint64_t)c->rows + 1) + 4ull * c->rows + 4ull * c->cols;
     out->kernel_launches = c->launches; out->sm_count = c->sm_count; out->grid = c->grid;
     out->replicas = (uint32_t)c->mats.size(); out->preprocess_seconds = c->preprocess_s;
+    out->layout = c->meta.narrow ? 1u : 0u;
     return HSB_OK;
 }
 
@@ -1360,13 +1364,21 @@ hsb_format *hsb_format_from_context(hsb_ctx *c) {
     f->M = c->meta;
     f->M.vals.resize(c->n_elems);
     f->M.cols16.resize(c->n_elems);
-    f->M.slice_rows.resize(c->n_slices * hsb::kLanes);
+    f->M.slice_rows.resize(c->meta.narrow ? 0 : c->n_slices * hsb::kLanes);
     const DeviceMatrix &d = c->mats[0];
     bool ok = cudaMemcpy(f->M.vals.data(), d.vals, c->n_elems * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
               cudaMemcpy(f->M.cols16.data(), d.cols, c->n_elems * 2, cudaMemcpyDeviceToHost) == cudaSuccess &&
-              cudaMemcpy(f->M.slice_rows.data(), d.slice_rows, c->n_slices * hsb::kLanes * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+              cudaMemcpy(f->M.slice_rows.data(), d.slice_rows, f->M.slice_rows.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
     if (!ok) { delete f; set_err(HSB_ECUDA, "download of the device format failed"); return nullptr; }
     return f;
+}
+
+int hsb_debug_profiler(hsb_ctx *c, int on) {
+    if (!c) return set_err(HSB_EINVAL, "null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    { int rc = quiesce(c); if (rc) return rc; }
+    CUDA_TRY(on ? cudaProfilerStart() : cudaProfilerStop());
+    return HSB_OK;
 }
 
 int hsb_debug_plan(hsb_ctx *c, uint32_t *steps, uint32_t *slices, size_t capacity) {

@@ -37,7 +37,7 @@ struct StreamRec {
     uint32_t pad_;
 };
 
-__device__ __forceinline__ uint32_t n_pieces(uint32_t n) { return (n + kMaxStreamLen - 1) / kMaxStreamLen; }
+__device__ __forceinline__ uint32_t n_pieces(uint32_t n, uint32_t max_len) { return (n + max_len - 1) / max_len; }
 
 // one thread per non-zero: key = ((part * T + tile) << 32) | row
 __global__ void k_keys(uint64_t nnz, uint32_t rows, const uint32_t *__restrict__ indptr,
@@ -58,19 +58,19 @@ __global__ void k_keys(uint64_t nnz, uint32_t rows, const uint32_t *__restrict__
     ids[e] = (uint32_t)e;
 }
 
-__global__ void k_piece_counts(uint32_t n_segs, const uint32_t *__restrict__ seg_len, uint32_t *__restrict__ pieces) {
+__global__ void k_piece_counts(uint32_t n_segs, const uint32_t *__restrict__ seg_len, uint32_t max_len, uint32_t *__restrict__ pieces) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n_segs) pieces[s] = n_pieces(seg_len[s]);
+    if (s < n_segs) pieces[s] = n_pieces(seg_len[s], max_len);
 }
 
 // one thread per segment: emit its lane streams (balanced piece lengths) and their sort keys
 __global__ void k_streams(uint32_t n_segs, const unsigned long long *__restrict__ seg_key,
                           const uint32_t *__restrict__ seg_len, const uint32_t *__restrict__ seg_start,
-                          const uint32_t *__restrict__ stream_off, StreamRec *__restrict__ recs,
+                          const uint32_t *__restrict__ stream_off, uint32_t max_len, StreamRec *__restrict__ recs,
                           unsigned long long *__restrict__ skeys, uint32_t *__restrict__ sids) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_segs) return;
-    const uint32_t n = seg_len[s], p = n_pieces(n), base = n / p, extra = n % p;
+    const uint32_t n = seg_len[s], p = n_pieces(n, max_len), base = n / p, extra = n % p;
     const unsigned long long tp = seg_key[s] >> 32;
     uint32_t src = seg_start[s], o = stream_off[s];
     for (uint32_t q = 0; q < p; q++, o++) {
@@ -103,8 +103,8 @@ __global__ void k_tile_slices(uint32_t NT, const uint32_t *__restrict__ tile_str
 // one thread per slice: its tile (binary search) and its step count
 __global__ void k_slice_steps(uint32_t n_slices, uint32_t NT, const uint32_t *__restrict__ tile_slice_begin,
                               const uint32_t *__restrict__ tile_stream_begin, const uint32_t *__restrict__ sids_sorted,
-                              const StreamRec *__restrict__ recs, uint32_t *__restrict__ slice_tile,
-                              uint32_t *__restrict__ slice_steps) {
+                              const StreamRec *__restrict__ recs, uint32_t slot_block, uint32_t row_units,
+                              uint32_t *__restrict__ slice_tile, uint32_t *__restrict__ slice_steps) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slices) return;
     uint32_t lo = 0, hi = NT;                         // last tile with tile_slice_begin[tile] <= s
@@ -116,12 +116,12 @@ __global__ void k_slice_steps(uint32_t n_slices, uint32_t NT, const uint32_t *__
     while (tile_slice_begin[lo + 1] <= s) lo++;
     const uint32_t first = tile_stream_begin[lo] + (s - tile_slice_begin[lo]) * kLanes;
     slice_tile[s] = lo;
-    slice_steps[s] = (recs[sids_sorted[first]].len + kSlotBlock - 1) / kSlotBlock;
+    slice_steps[s] = (recs[sids_sorted[first]].len + slot_block - 1) / slot_block + row_units;   // narrow: + the row unit
 }
 
 // one thread per (tile, c): cnt_ge[c] = slices of the tile with more than c steps (slices are sorted)
 __global__ void k_cnt_ge(uint32_t NT, const uint32_t *__restrict__ tile_slice_begin,
-                         const uint32_t *__restrict__ slice_steps, uint32_t *__restrict__ cnt_ge) {
+                         const uint32_t *__restrict__ slice_steps, uint32_t row_units, uint32_t *__restrict__ cnt_ge) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NT * 32u) return;
     const uint32_t tp = i >> 5, c = i & 31u;
@@ -129,7 +129,7 @@ __global__ void k_cnt_ge(uint32_t NT, const uint32_t *__restrict__ tile_slice_be
     const uint32_t b = lo;
     while (lo < hi) {                                  // first slice with steps <= c
         uint32_t mid = (lo + hi) >> 1;
-        if (slice_steps[mid] > c) lo = mid + 1; else hi = mid;
+        if (slice_steps[mid] - row_units > c) lo = mid + 1; else hi = mid;
     }
     cnt_ge[i] = lo - b;
 }
@@ -141,7 +141,7 @@ __global__ void k_fill(uint32_t n_slices, uint32_t rows, uint32_t tile_cols, uin
                        const uint32_t *__restrict__ sids_sorted, const StreamRec *__restrict__ recs,
                        const uint32_t *__restrict__ ids_sorted, const uint32_t *__restrict__ indices,
                        const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals, uint16_t *__restrict__ cols16,
-                       uint32_t *__restrict__ slice_rows) {
+                       uint32_t *__restrict__ slice_rows, int narrow) {
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (s >= n_slices) return;
     const uint32_t tp = slice_tile[s];
@@ -151,8 +151,9 @@ __global__ void k_fill(uint32_t n_slices, uint32_t rows, uint32_t tile_cols, uin
         const StreamRec r = recs[sids_sorted[i]];
         row = r.row; len = r.len; src = r.src;
     }
-    slice_rows[(size_t)s * kLanes + lane] = row;
-    const size_t base = (size_t)slice_off[s] * kStepElems;
+    // row ids: wide layout in slice_rows, narrow layout in the slice's leading row unit (column ids stay 0)
+    const size_t base = (size_t)slice_off[s] * (narrow ? kUnitElems : kStepElems);
+    if (narrow) vals[base + lane] = row; else slice_rows[(size_t)s * kLanes + lane] = row;
     const uint32_t col_base = (tp % T) * tile_cols;
     for (uint32_t k = 0; k < len; k++) {
         // per-lane rotation of the stream: neighbouring lanes that walk the same dense row start
@@ -160,7 +161,8 @@ __global__ void k_fill(uint32_t n_slices, uint32_t rows, uint32_t tile_cols, uin
         uint32_t from = k + lane;
         from = from >= len ? from % len : from;
         const uint32_t e = ids_sorted[src + from];
-        const size_t at = base + (size_t)(k / kSlotBlock) * kStepElems + (size_t)lane * kSlotBlock + (k % kSlotBlock);
+        const size_t at = narrow ? base + (size_t)(1 + k) * kUnitElems + lane
+                                 : base + (size_t)(k / kSlotBlock) * kStepElems + (size_t)lane * kSlotBlock + (k % kSlotBlock);
         vals[at] = vals_in[e];
         cols16[at] = (uint16_t)(indices[e] - col_base + kColBias);
     }
@@ -188,7 +190,9 @@ cudaError_t build_tiled_gpu(uint32_t rows, uint32_t cols, uint64_t nnz, const ui
                             std::string *err) {
     auto fail = [&](const char *m) { if (err) *err = m; return cudaErrorInvalidValue; };
     if (tile_cols == 0 || tile_cols > kMaxTileCols || (tile_cols & 7u)) return fail("bad tile_cols");
-    if (nnz >= (1ull << 32)) return fail("nnz must fit 32 bits");
+    // the device-wide sorts and scans take 32-bit signed item counts, and step / unit offsets (at most 2 per
+    // non-zero) are 32-bit exclusive sums
+    if (nnz > 0x7FFFFFFFull) return fail("more than 2^31 - 1 non-zeros in one matrix (shard it by row blocks)");
     TiledMatrix &M = *meta;
     M = TiledMatrix();
     M.rows = rows; M.cols = cols; M.nnz = nnz;
@@ -253,10 +257,14 @@ cudaError_t build_tiled_gpu(uint32_t rows, uint32_t cols, uint64_t nnz, const ui
     GF_TRY(cudaStreamSynchronize(stream));
     if (h_bad) return fail("column index out of range");
 
+    // layout (tile_format.h): narrow when the segments are nearly all one or two entries long
+    M.narrow = choose_narrow(nnz, n_segs);
+    const uint32_t max_len = M.narrow ? kNarrowMaxLen : kMaxStreamLen;
+    const uint32_t slot_block = M.narrow ? 1u : (uint32_t)kSlotBlock, row_units = M.narrow ? 1u : 0u;
     uint32_t *seg_start = nullptr, *pieces = nullptr, *stream_off = nullptr;
     GF_TRY(sc.get(&seg_start, n_segs + 1)); GF_TRY(sc.get(&pieces, n_segs + 1)); GF_TRY(sc.get(&stream_off, n_segs + 1));
     GF_TRY(cudaMemsetAsync(pieces + n_segs, 0, 4, stream));
-    k_piece_counts<<<blocks(n_segs), TB, 0, stream>>>(n_segs, seg_len, pieces);
+    k_piece_counts<<<blocks(n_segs), TB, 0, stream>>>(n_segs, seg_len, max_len, pieces);
     GF_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, seg_len, seg_start, (int)n_segs, stream));
     GF_TRY(ensure_tmp(need));
     GF_TRY(cub::DeviceScan::ExclusiveSum(tmp, need, seg_len, seg_start, (int)n_segs, stream));
@@ -272,7 +280,7 @@ cudaError_t build_tiled_gpu(uint32_t rows, uint32_t cols, uint64_t nnz, const ui
     uint32_t *sids = nullptr, *sids_s = nullptr;
     GF_TRY(sc.get(&recs, n_streams)); GF_TRY(sc.get(&skeys, n_streams)); GF_TRY(sc.get(&skeys_s, n_streams));
     GF_TRY(sc.get(&sids, n_streams)); GF_TRY(sc.get(&sids_s, n_streams));
-    k_streams<<<blocks(n_segs), TB, 0, stream>>>(n_segs, seg_key, seg_len, seg_start, stream_off, recs, skeys, sids);
+    k_streams<<<blocks(n_segs), TB, 0, stream>>>(n_segs, seg_key, seg_len, seg_start, stream_off, max_len, recs, skeys, sids);
     const int skey_bits = 8 + bits_for(NT);
     GF_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, skeys, skeys_s, sids, sids_s, (int)n_streams, 0, skey_bits, stream));
     GF_TRY(ensure_tmp(need));
@@ -294,11 +302,11 @@ cudaError_t build_tiled_gpu(uint32_t rows, uint32_t cols, uint64_t nnz, const ui
     GF_TRY(sc.get(&slice_tile, n_slices)); GF_TRY(sc.get(&slice_steps, n_slices + 1)); GF_TRY(sc.get(&slice_off, n_slices + 1));
     GF_TRY(sc.get(&cnt_ge, (size_t)NT * 32));
     GF_TRY(cudaMemsetAsync(slice_steps + n_slices, 0, 4, stream));
-    k_slice_steps<<<blocks(n_slices), TB, 0, stream>>>(n_slices, NT, tile_slice_begin, tile_stream_begin, sids_s, recs, slice_tile, slice_steps);
+    k_slice_steps<<<blocks(n_slices), TB, 0, stream>>>(n_slices, NT, tile_slice_begin, tile_stream_begin, sids_s, recs, slot_block, row_units, slice_tile, slice_steps);
     GF_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, slice_steps, slice_off, (int)n_slices + 1, stream));
     GF_TRY(ensure_tmp(need));
     GF_TRY(cub::DeviceScan::ExclusiveSum(tmp, need, slice_steps, slice_off, (int)n_slices + 1, stream));
-    k_cnt_ge<<<blocks((uint64_t)NT * 32), TB, 0, stream>>>(NT, tile_slice_begin, slice_steps, cnt_ge);
+    k_cnt_ge<<<blocks((uint64_t)NT * 32), TB, 0, stream>>>(NT, tile_slice_begin, slice_steps, row_units, cnt_ge);
     uint32_t n_steps = 0;
     GF_TRY(cudaMemcpyAsync(&n_steps, slice_off + n_slices, 4, cudaMemcpyDeviceToHost, stream));
 
@@ -312,15 +320,15 @@ cudaError_t build_tiled_gpu(uint32_t rows, uint32_t cols, uint64_t nnz, const ui
     GF_TRY(cudaStreamSynchronize(stream));
 
     // ---- stage C: fill the slices -------------------------------------------------------------
-    const size_t n_elems = (size_t)n_steps * kStepElems;
+    const size_t n_elems = (size_t)n_steps * M.step_elems();
     GF_TRY(dalloc(&out->vals, n_elems + 4));
     GF_TRY(dalloc(&out->cols, n_elems + 8));
-    GF_TRY(dalloc(&out->slice_rows, (size_t)n_slices * kLanes + 4));
+    GF_TRY(dalloc(&out->slice_rows, (M.narrow ? 0 : (size_t)n_slices * kLanes) + 4));
     GF_TRY(cudaMemsetAsync(out->vals, 0, n_elems * 4, stream));
     GF_TRY(cudaMemsetAsync(out->cols, 0, n_elems * 2, stream));                 // kPadCol == 0
     k_fill<<<blocks((uint64_t)n_slices * 32), TB, 0, stream>>>(n_slices, rows, tile_cols, T, slice_tile, slice_off,
                                                              tile_slice_begin, tile_stream_begin, sids_s, recs, ids_s,
-                                                             d_indices, d_vals, out->vals, out->cols, out->slice_rows);
+                                                             d_indices, d_vals, out->vals, out->cols, out->slice_rows, M.narrow ? 1 : 0);
     GF_TRY(cudaGetLastError());
     GF_TRY(cudaStreamSynchronize(stream));
     out->n_elems = n_elems; out->n_slices = n_slices; out->n_streams = n_streams;

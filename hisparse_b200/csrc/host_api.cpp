@@ -31,6 +31,7 @@ int hsb_format_stats(const hsb_format *f, hsb_stats *out) {
     out->nnz = M.nnz; out->rows = M.rows; out->cols = M.cols; out->n_row_parts = M.n_row_parts;
     out->n_col_tiles = M.n_col_tiles; out->tile_cols = M.tile_cols; out->n_slices = M.n_slices();
     out->n_streams = M.n_streams; out->n_elems = M.n_elems(); out->format_bytes = M.format_bytes();
+    out->layout = M.narrow ? 1u : 0u;
     out->algorithmic_bytes = 8ull * M.nnz + 4ull * ((uint64_t)M.rows + 1) + 4ull * M.rows + 4ull * M.cols;
     return HSB_OK;
 }
@@ -78,17 +79,20 @@ int hsb_format_expand(const hsb_format *f, uint32_t *indptr, uint32_t *indices, 
             for (uint32_t s = td.slice_begin; s < td.slice_end; s++) {
                 const hsb::SliceDesc &sd = M.slices[s];
                 if ((sd.tile_steps >> 8) != ti) return HSB_EINVAL;
-                const uint32_t steps = sd.tile_steps & 0xFFu;
-                if (steps == 0 || steps > hsb::kMaxStreamLen / hsb::kSlotBlock || steps > prev_steps) return HSB_EINVAL;
+                const uint32_t steps = sd.tile_steps & 0xFFu;        // narrow layout: 1 row unit + L step units
+                const uint32_t max_steps = M.narrow ? 1 + hsb::kNarrowMaxLen : hsb::kMaxStreamLen / hsb::kSlotBlock;
+                if (steps <= (M.narrow ? 1u : 0u) || steps > max_steps || steps > prev_steps) return HSB_EINVAL;
                 prev_steps = steps;                                  // sorted by length inside a tile
-                const size_t base = (size_t)sd.off * hsb::kStepElems;
-                if (base + (size_t)steps * hsb::kStepElems > M.vals.size()) return HSB_EINVAL;
+                const size_t base = (size_t)sd.off * M.step_elems();
+                if (base + (size_t)steps * M.step_elems() > M.vals.size()) return HSB_EINVAL;
+                const uint32_t slots = M.narrow ? steps - 1 : steps * hsb::kSlotBlock;
                 for (int lane = 0; lane < hsb::kLanes; lane++) {
-                    const uint32_t row = M.slice_rows[(size_t)s * hsb::kLanes + lane];
+                    if (M.narrow && M.cols16[base + lane] != hsb::kPadCol) return HSB_EINVAL;       // row unit: no column ids
+                    const uint32_t row = M.narrow ? M.vals[base + lane] : M.slice_rows[(size_t)s * hsb::kLanes + lane];
                     bool ended = false;
                     uint32_t len = 0;
-                    for (uint32_t k = 0; k < steps * hsb::kSlotBlock; k++) {
-                        const size_t e = hsb::slice_elem(base, lane, k);
+                    for (uint32_t k = 0; k < slots; k++) {
+                        const size_t e = M.narrow ? base + (size_t)(1 + k) * hsb::kUnitElems + lane : hsb::slice_elem(base, lane, k);
                         const uint16_t c16 = M.cols16[e];
                         if (c16 == hsb::kPadCol) {                   // padding: zero value, and only at the tail
                             if (M.vals[e]) return HSB_EINVAL;

@@ -75,6 +75,24 @@ __device__ __forceinline__ uint2 ldg_stream64(const uint2 *p) {
 #endif
     return r;
 }
+__device__ __forceinline__ uint32_t ldg_stream32(const uint32_t *p) {
+    uint32_t r;
+#if HSB_L2_HINTS
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(policy_evict_first()));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+#endif
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream16(const uint16_t *p) {
+    uint16_t r;
+#if HSB_L2_HINTS
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(r) : "l"(p), "l"(policy_evict_first()));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+#endif
+    return r;
+}
 // Bounded spin on a sequence flag another engine writes (a stream memory operation on a copy stream, a peer
 // GPU's kernel): true once (int)(flag - val) >= 0. kFlagPolls polls of ~1 us, then give up rather than hang
 // the GPU: the caller raises the error flag and SKIPS its work, so a stale vector is never multiplied.
@@ -349,7 +367,82 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, uint64_t *bar,
     if (left != steps_of(cnt, sl) && sl < n_slices) flush();
 }
 
+// Narrow layout (hypersparse matrices, tile_format.h): one warp streams units [ta, tb) of a tile, 32 elements
+// each (128 B of value words + 64 B of column ids). A slice is a ROW UNIT -- lane l's value word is the matrix
+// row of its stream -- followed by L(slice) step units, one slot per lane; shares begin and end at slice
+// boundaries. Row ids, values and column ids all arrive through the same kNarrowRing-deep register ring, so the
+// latency of none of them is exposed, however short the slices are (the wide layout's separate row-id loads
+// were 40 % of all stall samples on a C5 shard, whose slices are one or two steps long).
 template <class A>
+__device__ __forceinline__ void stream_units_narrow(const SpmvParams &p, uint64_t *bar, uint32_t parity, uint32_t cnt,
+                                                    uint32_t unit_begin, uint32_t ta, uint32_t tb, uint32_t first_slice,
+                                                    uint32_t lane, bool first_segment, const volatile uint32_t *abort_flag) {
+    uint32_t remaining = tb - ta;
+    const size_t base = (size_t)(unit_begin + ta) * kUnitElems + lane;
+    const uint32_t *vp = p.vals + base;
+    const uint16_t *cp = p.cols + base;
+    uint32_t vb[kNarrowRing], cb[kNarrowRing];
+#pragma unroll
+    for (int j = 0; j < kNarrowRing; j++)
+        if ((uint32_t)j < remaining) {
+            vb[j] = ldg_stream32(vp + j * kUnitElems);
+            cb[j] = ldg_stream16(cp + j * kUnitElems);
+        }
+    vp += kNarrowRing * kUnitElems;
+    cp += kNarrowRing * kUnitElems;
+
+    mbar_wait(bar, parity);
+    if (p.timeline && first_segment && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[(size_t)(p.seq & 255u) * 8 + 4] = globaltimer();
+    if (!remaining || *abort_flag) return;
+
+    uint32_t xs_base = smem_u32(xs);
+    asm volatile("" : "+r"(xs_base));
+    A acc;
+    acc.clear();
+    uint32_t sl = first_slice, left = 0, row = 0;
+    auto consume = [&](uint32_t v, uint32_t c) {
+        if (left == 0) {                                       // warp-uniform: a row unit opens slice sl
+            row = v;
+            left = steps_of(cnt, sl);
+            return;
+        }
+        uint32_t xv;
+        asm("{\n\t.reg .u32 t;\n\tmad.lo.u32 t, %1, 4, %2;\n\tld.shared.u32 %0, [t];\n\t}" : "=r"(xv) : "r"(c), "r"(xs_base));
+        acc.mac(v, xv);
+        if (--left == 0) {                                     // the slice is complete: one row update per lane stream
+            typename A::acc_t t = acc.total();
+            if (__all_sync(0xFFFFFFFFu, row == __shfl_sync(0xFFFFFFFFu, row, 0))) {
+                t = A::warp_sum(t);
+                if (lane == 0) A::emit(p.acc, row, t);
+            } else {
+                A::emit(p.acc, row, t);
+            }
+            acc.clear();
+            sl++;
+        }
+    };
+    while (remaining >= (uint32_t)kNarrowRing) {
+#pragma unroll
+        for (int j = 0; j < kNarrowRing; j++) {
+            const uint32_t v = vb[j], c = cb[j];
+            if (remaining > (uint32_t)(kNarrowRing + j)) {
+                vb[j] = ldg_stream32(vp + j * kUnitElems);
+                cb[j] = ldg_stream16(cp + j * kUnitElems);
+            }
+            consume(v, c);
+        }
+        vp += kNarrowRing * kUnitElems;
+        cp += kNarrowRing * kUnitElems;
+        remaining -= kNarrowRing;
+    }
+#pragma unroll
+    for (int j = 0; j < kNarrowRing - 1; j++)
+        if ((uint32_t)j < remaining) consume(vb[j], cb[j]);
+}
+
+// kNarrow selects the layout at compile time: the two streaming loops live in separate kernels, so that each gets
+// the whole 64-register budget of a 1024-thread CTA for its own prefetch ring
+template <class A, bool kNarrow>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const SpmvParams p) {
     unsigned char *smem_raw = reinterpret_cast<unsigned char *>(xs);
     __shared__ __align__(8) uint64_t bar;
@@ -428,7 +521,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
             // this warp's equal-cost share of the segment (host plan)
             const uint32_t ta = __ldg(&sg->warp_t[warp]), tb = __ldg(&sg->warp_t[warp + 1]);
             const uint32_t first_slice = __ldg(&sg->warp_slice[warp]);
-            stream_steps<A>(p, &bar, parity, cnt, h1.y, h1.z, h1.w, ta, tb, first_slice, lane, g == g0, &abort_flag);
+            if (kNarrow) stream_units_narrow<A>(p, &bar, parity, cnt, h1.w, ta, tb, first_slice, lane, g == g0, &abort_flag);
+            else stream_steps<A>(p, &bar, parity, cnt, h1.y, h1.z, h1.w, ta, tb, first_slice, lane, g == g0, &abort_flag);
             parity ^= 1u;
             if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * (kWarps + 2) + warp] = clock64() - t_start;
             __syncthreads();                                       // everyone is done with this x tile
@@ -561,11 +655,13 @@ cudaError_t launch_axpb(int arith, void *acc, uint32_t *y, uint32_t *x_next, uin
 
 cudaError_t configure_kernels(int sm_count) {
     if (sm_count > 0) g_sm_count = sm_count;
-    cudaError_t e = cudaFuncSetAttribute(spmv_tiles_kernel<FixedArith>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemBytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(spmv_tiles_kernel<FloatArith>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)kSmemBytes);
+    const void *kernels[] = {(const void *)spmv_tiles_kernel<FixedArith, false>, (const void *)spmv_tiles_kernel<FloatArith, false>,
+                             (const void *)spmv_tiles_kernel<FixedArith, true>, (const void *)spmv_tiles_kernel<FloatArith, true>};
+    for (const void *k : kernels) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, uint32_t smem_bytes, cudaStream_t stream) {
@@ -580,8 +676,12 @@ cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, uint32_t smem_
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (arith == kArithFixed) return cudaLaunchKernelEx(&cfg, spmv_tiles_kernel<FixedArith>, p);
-    return cudaLaunchKernelEx(&cfg, spmv_tiles_kernel<FloatArith>, p);
+    if (p.narrow) {
+        if (arith == kArithFixed) return cudaLaunchKernelEx(&cfg, spmv_tiles_kernel<FixedArith, true>, p);
+        return cudaLaunchKernelEx(&cfg, spmv_tiles_kernel<FloatArith, true>, p);
+    }
+    if (arith == kArithFixed) return cudaLaunchKernelEx(&cfg, spmv_tiles_kernel<FixedArith, false>, p);
+    return cudaLaunchKernelEx(&cfg, spmv_tiles_kernel<FloatArith, false>, p);
 }
 
 cudaError_t launch_drain(int arith, void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end,

@@ -59,6 +59,10 @@ constexpr int kPrefetch = HSB_PREFETCH;              // slice steps in flight pe
 #define HSB_ROW_AHEAD 1
 #endif
 constexpr int kRowAhead = HSB_ROW_AHEAD;             // slices whose row ids are loaded ahead of their use
+#ifndef HSB_NARROW_RING
+#define HSB_NARROW_RING 10
+#endif
+constexpr int kNarrowRing = HSB_NARROW_RING;         // narrow layout: units (192 B per warp) in flight per warp
 
 struct SpmvParams {
     const uint32_t *vals;
@@ -100,7 +104,9 @@ struct SpmvParams {
     // whole grid is through, raises this rank's arrival flag there -- the gather of y is the drain's epilogue.
     const struct GatherTargets *gather;   // device-resident table, or null
     uint32_t gather_seq;          // value the arrival flags receive: gathered drains so far, this one included
-    uint32_t acquire;             // 1: flag waits end in fence.acq_rel.sys (+ fence.proxy.async before the x TMA)
+    uint32_t acquire;             // 1: flag waits are acquire loads (+ fence.proxy.async before the x TMA)
+    uint32_t narrow;              // 1: the matrix is in the narrow layout (tile_format.h): units of 32 elements, a row
+                                  // unit in front of every slice, shares cut at slice boundaries; slice_rows unused
 };
 
 constexpr int kMaxPeers = 16;

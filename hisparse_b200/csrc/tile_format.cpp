@@ -47,6 +47,11 @@ uint32_t choose_tile_cols(uint32_t cols, uint32_t rows, uint64_t nnz) {
     return std::min(w, kMaxTileCols);
 }
 
+bool choose_narrow(uint64_t nnz, uint64_t n_segments) {
+    if (const char *e = std::getenv("HSB_NARROW")) return std::atoi(e) != 0;        // A/B aid
+    return n_segments > 0 && (double)nnz < kNarrowBelow * (double)n_segments;
+}
+
 namespace {
 
 struct Slab {
@@ -71,8 +76,8 @@ template <class F> void parallel_for(size_t n, int n_threads, F f) {
     for (auto &x : th) x.join();
 }
 
-// number of lane streams a segment of n non-zeros is cut into, and the length of piece q
-inline uint32_t n_pieces(uint32_t n) { return (n + kMaxStreamLen - 1) / kMaxStreamLen; }
+// number of lane streams a segment of n non-zeros is cut into (at most max_len each), and the length of piece q
+inline uint32_t n_pieces(uint32_t n, uint32_t max_len) { return (n + max_len - 1) / max_len; }
 inline uint32_t piece_len(uint32_t n, uint32_t pieces, uint32_t q) { return n / pieces + (q < n % pieces ? 1u : 0u); }
 
 }  // namespace
@@ -180,11 +185,17 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
     });
 
     // ---- stage B -------------------------------------------------------------------------
+    // layout: wide (4 slots per lane and step, row ids in slice_rows) or narrow (1 slot per lane and unit, a
+    // row unit in front of every slice) -- see tile_format.h
+    M.narrow = choose_narrow(nnz, tile_seg0[NT]);
+    const uint32_t max_len = M.narrow ? kNarrowMaxLen : kMaxStreamLen;
+    const uint32_t slot_block = M.narrow ? 1u : (uint32_t)kSlotBlock, row_units = M.narrow ? 1u : 0u;
+    const uint32_t step_elems = M.step_elems();
     std::vector<uint64_t> t_streams(NT + 1, 0), t_slices(NT + 1, 0), t_steps(NT + 1, 0);
     auto tile_plan = [&](size_t ti, uint32_t *hist /*[kMaxStreamLen+1]*/) {
         std::fill(hist, hist + kMaxStreamLen + 1, 0u);
         for (uint64_t g = tile_seg0[ti]; g < tile_seg0[ti + 1]; g++) {
-            uint32_t n = a_seg_len[g], p = n_pieces(n);
+            uint32_t n = a_seg_len[g], p = n_pieces(n, max_len);
             hist[n / p] += p - n % p;
             if (n % p) hist[n / p + 1] += n % p;
         }
@@ -203,7 +214,7 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
             if (first_start < idx + h) {
                 uint64_t n_start = (idx + h - first_start + kLanes - 1) / kLanes;
                 slices += n_start;
-                steps += n_start * ((len + kSlotBlock - 1) / kSlotBlock);
+                steps += n_start * ((len + slot_block - 1) / slot_block + row_units);
             }
             idx += h;
             ns += h;
@@ -218,9 +229,9 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
     M.n_streams = t_streams[NT];
     const size_t NSL = (size_t)t_slices[NT];
     M.slices.assign(NSL, SliceDesc{0, 0});
-    M.slice_rows.assign(NSL * kLanes, rows);
-    M.vals.assign((size_t)t_steps[NT] * kStepElems, 0u);
-    M.cols16.assign((size_t)t_steps[NT] * kStepElems, kPadCol);
+    if (!M.narrow) M.slice_rows.assign(NSL * kLanes, rows);
+    M.vals.assign((size_t)t_steps[NT] * step_elems, 0u);
+    M.cols16.assign((size_t)t_steps[NT] * step_elems, kPadCol);
     M.tiles.resize(NT);
     M.part_slice_begin.assign(M.n_row_parts + 1, 0);
     std::vector<Stream> streams((size_t)t_streams[NT]);
@@ -234,7 +245,7 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
         for (uint32_t len = kMaxStreamLen; len >= 1; len--) { start[len] = run; run += hist[len]; }
         uint64_t src = tile_nnz0[ti];
         for (uint64_t g = tile_seg0[ti]; g < tile_seg0[ti + 1]; g++) {
-            uint32_t n = a_seg_len[g], p = n_pieces(n);
+            uint32_t n = a_seg_len[g], p = n_pieces(n, max_len);
             for (uint32_t q = 0; q < p; q++) {
                 uint32_t l = piece_len(n, p, q);
                 streams[start[l]++] = Stream{a_seg_row[g], l, src};
@@ -253,10 +264,10 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
         td.step_begin = (uint32_t)t_steps[ti];
         uint64_t off = t_steps[ti];
         for (uint64_t s = t_slices[ti], i = t_streams[ti]; s < t_slices[ti + 1]; s++, i += kLanes) {
-            uint32_t steps = (streams[i].len + kSlotBlock - 1) / kSlotBlock;
+            uint32_t steps = (streams[i].len + slot_block - 1) / slot_block;
             M.slices[s].off = (uint32_t)off;
-            M.slices[s].tile_steps = ((uint32_t)ti << 8) | steps;
-            off += steps;
+            M.slices[s].tile_steps = ((uint32_t)ti << 8) | (steps + row_units);
+            off += steps + row_units;
             for (uint32_t c = 0; c < steps; c++) td.cnt_ge[c]++;
         }
     });
@@ -276,14 +287,15 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
         for (size_t s = blk * kBlock; s < std::min(NSL, (blk + 1) * kBlock); s++) {
             const size_t ti = M.slices[s].tile_steps >> 8;
             const uint64_t i0 = t_streams[ti] + (s - t_slices[ti]) * kLanes;
-            const size_t base = (size_t)M.slices[s].off * kStepElems;
+            const size_t base = (size_t)M.slices[s].off * step_elems;
             uint32_t rem[kLanes], maxlen = 0;
             for (int lane = 0; lane < kLanes; lane++) {
                 rem[lane] = 0;
                 uint64_t i = i0 + lane;
+                if (M.narrow) M.vals[base + lane] = i < t_streams[ti + 1] ? streams[i].row : rows;     // the row unit
                 if (i >= t_streams[ti + 1]) continue;
                 const Stream &st = streams[i];
-                M.slice_rows[s * kLanes + lane] = st.row;
+                if (!M.narrow) M.slice_rows[s * kLanes + lane] = st.row;
                 rem[lane] = st.len;
                 maxlen = std::max(maxlen, st.len);
                 for (uint32_t k = 0; k < st.len; k++) {
@@ -304,7 +316,7 @@ bool build_tiled(uint32_t rows, uint32_t cols, const uint32_t *indptr, const uin
                     for (uint32_t c = 0; c < window; c++)
                         if (!((busy >> (lc[c] & 31u)) & 1u)) { pick = c; break; }
                     busy |= 1u << (lc[pick] & 31u);
-                    const size_t e = slice_elem(base, lane, k);
+                    const size_t e = M.narrow ? base + (size_t)(1 + k) * kUnitElems + lane : slice_elem(base, lane, k);
                     M.vals[e] = lv[pick];
                     M.cols16[e] = lc[pick];
                     lv[pick] = lv[n - 1];                       // order inside a stream is free
@@ -372,6 +384,7 @@ uint32_t step_at_cost(const TiledMatrix &m, const TileDesc &td, double w) {
     uint32_t steps = sd.tile_steps & 0xFFu, s_before = sd.off - td.step_begin;
     double inside = w - start_cost(lo) - B;
     uint32_t k = inside <= 0 ? 0u : (uint32_t)std::min<double>(steps, inside + 0.5);
+    if (m.narrow) k = 2 * k >= steps ? steps : 0u;             // narrow layout: shares begin and end at slice boundaries
     return s_before + k;
 }
 uint32_t tile_steps_total(const TiledMatrix &m, const TileDesc &td) {

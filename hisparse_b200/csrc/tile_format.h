@@ -23,6 +23,21 @@
 //     no in-band markers are needed.
 //
 // 6 bytes per stored non-zero slot + 4 bytes per lane stream + 8 bytes per slice.
+//
+// NARROW layout (hypersparse matrices: on average fewer than kNarrowBelow non-zeros per (row, tile) segment --
+// the C5 shards, where nearly every segment is a single entry). Rounding every stream up to 4 slots would
+// double the bytes, and a slice would be over before the load of its row ids has returned. So:
+//   * the unit of the stream is 32 elements (one per lane): 128 B of value words + 64 B of column ids;
+//   * lane streams hold at most kNarrowMaxLen non-zeros; a slice of 32 streams, padded to its longest stream L,
+//     is ONE ROW UNIT (the value word of lane l is the matrix row of stream l, `rows` for an unused lane; column
+//     ids 0) followed by L step units (slot k of every lane). The row ids travel IN the stream, so the kernel's
+//     prefetch ring covers their latency like that of the values;
+//   * slice_rows is empty; SliceDesc.off / TileDesc.step_begin / cnt_ge count UNITS: tile-relative slice i has
+//     L(i) = #{c : cnt_ge[c] > i} step units and starts at unit i + sum_c min(i, cnt_ge[c]); SliceDesc's low byte
+//     holds 1 + L;
+//   * warp shares and CTA segments are cut at slice boundaries only (slices are at most 33 units long).
+// 6 bytes per stored slot, padding only up to the longest of 32 length-sorted streams: C5 shard 8.6 B per non-zero
+// against 16.3 in the wide layout.
 #ifndef HISPARSE_B200_TILE_FORMAT_H_
 #define HISPARSE_B200_TILE_FORMAT_H_
 
@@ -48,6 +63,9 @@ constexpr uint32_t kMaxStreamLen = 128;                  // non-zeros per lane s
 constexpr uint32_t kMaxTileCols = 57344;                 // 224 KB of x in shared memory (of 227 KB per CTA), 16-bit ids
 constexpr uint16_t kColBias = 8;                         // stored column id = tile-local column + 8 ...
 constexpr uint16_t kPadCol = 0;                          // ... so that id 0 (padding slots) can point at a constant 0 word
+constexpr int kUnitElems = kLanes;                       // narrow layout: elements per unit (one slot per lane)
+constexpr uint32_t kNarrowMaxLen = 32;                   // narrow layout: non-zeros per lane stream (cnt_ge has 32 entries)
+constexpr double kNarrowBelow = 2.5;                     // average non-zeros per (row, tile) segment below which the narrow layout is used
 
 struct SliceDesc {
     uint32_t off;           // element offset of the slice / kStepElems
@@ -74,12 +92,14 @@ struct TiledMatrix {
     uint64_t nnz = 0;
     uint32_t rows_per_part = 0, n_row_parts = 0, n_col_tiles = 0, tile_cols = 0;
     uint64_t n_streams = 0;                 // lane streams (row segments after splitting)
+    bool narrow = false;                    // narrow layout (see the header comment): units of 32 elements, row ids in the stream
     std::vector<uint32_t> vals;             // n_elems words
     std::vector<uint16_t> cols16;           // n_elems local column ids
     std::vector<SliceDesc> slices;          // n_slices (host side only: planning and inspection)
     std::vector<uint32_t> slice_rows;       // n_slices * 32 ; `rows` (one past the end) marks an unused lane
     std::vector<TileDesc> tiles;            // n_row_parts * n_col_tiles, row-partition major
     std::vector<uint32_t> part_slice_begin; // n_row_parts + 1
+    uint32_t step_elems() const { return narrow ? (uint32_t)kUnitElems : (uint32_t)kStepElems; }   // elements per step / unit
     size_t n_slices() const { return slices.size(); }
     size_t n_elems() const { return vals.size(); }
     size_t format_bytes() const {
@@ -92,6 +112,10 @@ struct TiledMatrix {
 inline size_t slice_elem(size_t base, int lane, uint32_t k) {
     return base + (size_t)(k / kSlotBlock) * kStepElems + (size_t)lane * kSlotBlock + (k % kSlotBlock);
 }
+
+// layout choice: narrow when the matrix has on average fewer than kNarrowBelow non-zeros per (row, tile) segment
+// (HSB_NARROW=0 / 1 forces the wide / narrow layout: A/B aid)
+bool choose_narrow(uint64_t nnz, uint64_t n_segments);
 
 // Choose a tile width (multiple of 8, widths equalised): one tile when x fits shared memory, otherwise tiles
 // of at most 44,000 columns, or 32,768 for hypersparse matrices (less than one entry per row and tile).

@@ -33,6 +33,47 @@ static int walk_plan_fixed(const hsb::TiledMatrix &M, uint32_t ctas, const uint3
                 if (!remaining) continue;
                 uint32_t sl = sg.warp_slice[w];
                 if (sl >= sg.n_slices) return HSB_EINVAL;
+                if (M.narrow) {
+                    // narrow layout (stream_units_narrow in the kernel): units of 32 elements; a share starts at the
+                    // row unit of slice sl and ends at a slice boundary; L(sl) step units follow every row unit
+                    if (sl + steps_before(sg.cnt_ge, sl) != ta) return HSB_EINVAL;          // not at a slice boundary
+                    const size_t ubase = (size_t)(sg.step_begin + ta) * hsb::kUnitElems;
+                    uint32_t nleft = 0, rows_of[hsb::kLanes] = {};
+                    unsigned long long lacc[hsb::kLanes] = {};
+                    for (uint32_t k = 0; k < remaining; k++) {
+                        const size_t ub = ubase + (size_t)k * hsb::kUnitElems;
+                        if (ub + hsb::kLanes > M.vals.size()) return HSB_EINVAL;
+                        if (nleft == 0) {                                                   // a row unit opens slice sl
+                            if (sl >= sg.n_slices) return HSB_EINVAL;
+                            for (int l = 0; l < hsb::kLanes; l++) {
+                                if (M.cols16[ub + l] != hsb::kPadCol || M.vals[ub + l] > M.rows) return HSB_EINVAL;
+                                rows_of[l] = M.vals[ub + l];
+                            }
+                            nleft = steps_of(sg.cnt_ge, sl);
+                            if (nleft == 0) return HSB_EINVAL;
+                            continue;
+                        }
+                        for (int l = 0; l < hsb::kLanes; l++) {
+                            const uint32_t id = M.cols16[ub + l];
+                            uint32_t xv = 0;
+                            if (id >= hsb::kColBias) {
+                                const uint32_t col = sg.col_base + id - hsb::kColBias;
+                                if (id - hsb::kColBias >= sg.col_count || col >= M.cols) return HSB_EINVAL;
+                                xv = x_words[col];
+                            } else if (id != hsb::kPadCol || M.vals[ub + l] != 0) {
+                                return HSB_EINVAL;
+                            }
+                            unsigned long long q = ((unsigned long long)M.vals[ub + l] * xv + 0x800000ull) >> 24;
+                            lacc[l] += std::min<unsigned long long>(q, 0xFFFFFFFFull);
+                        }
+                        if (--nleft == 0) {
+                            for (int m = 0; m < hsb::kLanes; m++) { acc[rows_of[m]] += lacc[m]; lacc[m] = 0; }
+                            sl++;
+                        }
+                    }
+                    if (nleft != 0) return HSB_EINVAL;                                       // the share ended inside a slice
+                    continue;
+                }
                 if (steps_before(sg.cnt_ge, sl) > ta || steps_before(sg.cnt_ge, sl + 1) <= ta) return HSB_EINVAL;   // wrong first slice
                 uint32_t left = steps_before(sg.cnt_ge, sl + 1) - ta;
                 const size_t base = (size_t)(sg.step_begin + ta) * hsb::kStepElems;

@@ -65,6 +65,8 @@ typedef struct hsb_stats {
     uint64_t kernel_launches;      /* kernels of this library launched so far on this context */
     uint32_t sm_count, grid;
     uint32_t replicas;
+    uint32_t layout;               /* 0: wide tile streams (4 slots per lane and step), 1: narrow (hypersparse matrices:
+                                      1 slot per lane and unit, row ids in the stream) -- csrc/tile_format.h */
     double preprocess_seconds;     /* host formatting time of the last upload ("Preprocessing" in benchmark.cpp:80-87) */
 } hsb_stats;
 
@@ -216,6 +218,9 @@ int hsb_debug_trace(hsb_ctx *ctx, unsigned long long *out, size_t capacity);
  * its drain share and published it, 4 CTA 0 has its x tile, 5 last CTA ended, 6 CTA 0 finished its matrix work. out == NULL arms (capacity != 0) / disarms.
  * Returns the number of the last launch. */
 int hsb_debug_timeline(hsb_ctx *ctx, unsigned long long *out, size_t capacity);
+/* Profiling aid: cudaProfilerStart (on != 0) / cudaProfilerStop around a range of calls, for
+ * `ncu --replay-mode app-range` (DRAM counters over a whole loop of overlapping launches). Synchronises first. */
+int hsb_debug_profiler(hsb_ctx *ctx, int on);
 /* Profiling aid: steps and slices the whole-matrix plan gives to every CTA. */
 int hsb_debug_plan(hsb_ctx *ctx, uint32_t *steps, uint32_t *slices, size_t capacity);
 /* raw device pointers / stream for callers that move x or y with NCCL (torch.distributed);

@@ -758,3 +758,67 @@ def test_reference_csim_harness_on_gpu(gpu, impl):
     for name in ("on basic dense matrix", "on basic sparse matrix", "on uniform 100K 10"):
         assert "------ Running test: " + name in out
     assert "datasets are not available" in r.stderr
+
+
+# ------------------------------------------------------------------------------------------
+# narrow layout (hypersparse matrices; csrc/tile_format.h): chosen automatically for singleton-dominated
+# matrices (tests/test_gpu_synth.py), FORCED here on ordinary ones, so that long rows (streams cut at 32),
+# row partitions, partition launches and the pipelined host-buffer path all run through the narrow kernel
+# ------------------------------------------------------------------------------------------
+NARROW_GPU_CASES = [
+    ("rmat_20000", lambda: matgen.rmat_csr(20000, 600000, 8), 0),
+    ("multi_tile_70000", lambda: matgen.random_csr(900, 70000, 0.003, 7), 0),
+    ("row_partitions", lambda: matgen.rmat_csr(20000, 300000, 9), 4096),
+    ("dense128", lambda: matgen.dense_csr(128, 128), 0),
+    ("one_long_row", lambda: (4, 70000, np.array([0, 0, 70000, 70000, 70001], np.uint32),
+                              np.concatenate([np.arange(70000), [3]]).astype(np.uint32),
+                              np.full(70001, 0.001, np.float32)), 0),
+    ("singletons_92_tiles", lambda: matgen.random_csr(30000, 3000000, 0.000004, 13), 0),
+]
+
+
+@pytest.mark.parametrize("name,make,rpp", NARROW_GPU_CASES, ids=[c[0] for c in NARROW_GPU_CASES])
+def test_narrow_layout_fixed_bit_exact(gpu, port, monkeypatch, name, make, rpp):
+    monkeypatch.setenv("HSB_NARROW", "1")
+    rows, cols, indptr, indices, data = make()
+    words = port.quantize((data * np.float32(0.5)).astype(np.float32))
+    rng = np.random.default_rng(3)
+    xs = [port.quantize(rng.random(cols, dtype=np.float32)) for _ in range(3)]
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    ctx.upload_matrix_csr(rows, cols, indptr, indices, words, rpp)
+    assert ctx.stats()["layout"] == 1
+    # the device-built narrow format decodes back to the CSR, with the host builder's geometry
+    ip, ix, vv = capi.Format.from_context(ctx).expand()
+    assert np.array_equal(ip, indptr)
+    r = np.repeat(np.arange(rows, dtype=np.int64), np.diff(indptr.astype(np.int64)))
+    a, b = np.lexsort((words, indices, r)), np.lexsort((vv, ix, r))
+    assert np.array_equal(indices[a], ix[b]) and np.array_equal(words[a], vv[b])
+    sg, sh = ctx.stats(), capi.Format(rows, cols, indptr, indices, words, rpp).stats()
+    for k in ("n_streams", "n_slices", "n_elems", "n_col_tiles", "layout"):
+        assert sg[k] == sh[k], k
+    # blocking, back-to-back (the end-of-launch drain), and one row partition at a time
+    ctx.upload_vector(xs[0]); ctx.spmv()
+    assert np.array_equal(ctx.download_result(), port.spmv_q824(indptr, indices, words, xs[0]))
+    ctx.upload_vector(xs[1]); ctx.spmv(); ctx.spmv(); ctx.spmv()
+    assert np.array_equal(ctx.download_result(), port.spmv_q824(indptr, indices, words, xs[1]))
+    if rpp:
+        ctx.upload_vector(xs[2])
+        nparts = (rows + rpp - 1) // rpp
+        for j in range(nparts):
+            ctx.spmv_row_partition(j, min(rpp, rows - j * rpp) // 16, 1, nparts, cols + (-cols) % 8)
+        assert np.array_equal(ctx.download_result(), port.spmv_q824(indptr, indices, words, xs[2]))
+    ctx.close()
+
+
+def test_narrow_layout_float(gpu, port, monkeypatch):
+    monkeypatch.setenv("HSB_NARROW", "1")
+    rows, cols, indptr, indices, data = matgen.rmat_csr(20000, 600000, 8, values="normal")
+    x = (np.random.default_rng(2).random(cols, dtype=np.float32) * 2 - 1).astype(np.float32)
+    ctx = capi.Context(0, "float_pob")
+    ctx.upload_matrix_csr(rows, cols, indptr, indices, data)
+    assert ctx.stats()["layout"] == 1
+    ctx.upload_vector(x)
+    ctx.spmv()
+    y = ctx.download_result()
+    ctx.close()
+    check_float(y, port, indptr, indices, data, x)

@@ -68,6 +68,8 @@ def test_tile_format_round_trip(name, mat, rpp, tile):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     # bytes: 6 per stored slot + 4 per lane stream slot + 8 per slice (+ tile table)
     assert st["format_bytes"] >= 6 * st["nnz"] and st["n_elems"] >= st["nnz"]
+    if st["layout"] == 1:       # narrow: one row unit per slice, padding only up to the longest of 32 sorted streams
+        assert st["n_elems"] <= 2 * st["nnz"] + 64 * st["n_slices"]
     assert st["n_streams"] <= max(1, rows * st["n_col_tiles"]) + st["nnz"] // 64 + 1
 
 
@@ -149,7 +151,7 @@ def test_plan_covers_every_step_once(name, make, tile_cols, ctas):
             assert a == pos and b > a, (name, tile, ranges[:4])
             pos = b
         total += pos
-    assert total * 128 == st["n_elems"]                    # all stored slots, nothing twice
+    assert total * (32 if st["layout"] == 1 else 128) == st["n_elems"]      # all stored slots, nothing twice
     # balance: no CTA gets more than ~1.5x the mean number of steps (+ one slice of slack)
     per_cta = np.bincount(rec[:, 0], weights=(rec[:, 3] - rec[:, 2]).astype(np.float64), minlength=ctas)
     busy = per_cta[per_cta > 0]
@@ -267,3 +269,47 @@ def test_plan_walk_bench_matrix(port):
     assert fmt.stats()["n_col_tiles"] == 3
     want = port.spmv_q824(ip2, indices, words, xw)
     assert np.array_equal(fmt.emulate_fixed(148, xw), want)
+
+
+# ------------------------------------------------------------------------------------------
+# narrow layout (hypersparse matrices): chosen automatically, and forced either way on the same inputs
+# ------------------------------------------------------------------------------------------
+def test_layout_choice():
+    q = hsoracle.Port().quantize
+    r, c, ip, ix, d = matgen.random_csr(30000, 3000000, 0.000004, 13)      # ~12 entries per row over 92 tiles: singletons
+    assert capi.Format(r, c, ip, ix, q(d), 0, 32768).stats()["layout"] == 1
+    r, c, ip, ix, d = matgen.rmat_csr(6000, 150000, 5)                      # 25 per row in one tile
+    assert capi.Format(r, c, ip, ix, q(d)).stats()["layout"] == 0
+
+
+NARROW_CASES = [
+    ("singletons", lambda: matgen.random_csr(30000, 3000000, 0.000004, 13), 0, 32768, 148),
+    ("rmat_forced", lambda: matgen.rmat_csr(6000, 150000, 5), 0, 0, 148),            # streams up to 32, hub rows split
+    ("dense_forced", lambda: matgen.dense_csr(128, 128), 0, 0, 37),
+    ("row_partitions_forced", lambda: matgen.rmat_csr(20000, 300000, 9), 4096, 8192, 148),
+    ("one_long_row_forced", lambda: (4, 70000, np.array([0, 0, 70000, 70000, 70001], np.uint32),
+                                     np.concatenate([np.arange(70000), [3]]).astype(np.uint32),
+                                     np.full(70001, 0.001, np.float32)), 0, 0, 148),
+    ("empty_rows_and_tiles", lambda: matgen.random_csr(500, 200000, 0.00002, 21), 0, 8192, 5),
+]
+
+
+@pytest.mark.parametrize("narrow", [1, 0])
+@pytest.mark.parametrize("name,make,rpp,tile_cols,ctas", NARROW_CASES, ids=[c[0] for c in NARROW_CASES])
+def test_both_layouts_round_trip_and_walk(port, monkeypatch, name, make, rpp, tile_cols, ctas, narrow):
+    monkeypatch.setenv("HSB_NARROW", str(narrow))
+    rows, cols, indptr, indices, data = make()
+    words = port.quantize(data)
+    x = port.quantize(np.random.default_rng(2).random(cols, dtype=np.float32))
+    fmt = capi.Format(rows, cols, indptr, indices, words, rpp, tile_cols)
+    st = fmt.stats()
+    assert st["layout"] == narrow
+    ip, ix, vv = fmt.expand()
+    assert np.array_equal(ip, indptr)
+    a, b = _canon(rows, indptr, indices, words), _canon(rows, ip, ix, vv)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # the plan hands out every unit exactly once, and (narrow) only whole slices
+    rec = fmt.plan(ctas)
+    total = sum(r[-1][1] for r in _steps_per_tile(fmt, rec).values())
+    assert total * (32 if narrow else 128) == st["n_elems"]
+    assert np.array_equal(fmt.emulate_fixed(ctas, x), port.spmv_q824(indptr, indices, words, x))

@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--replicas", type=int, default=0)
     ap.add_argument("--gpu-format", action="store_true")
+    ap.add_argument("--range", type=int, default=0,
+                    help="N back-to-back SpMVs inside ONE cudaProfilerStart/Stop range (ncu --replay-mode app-range)")
     a = ap.parse_args()
     rows, cols, indptr, indices, data = make(a.config)
     r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
@@ -53,6 +55,14 @@ def main():
             st["algorithmic_bytes"] / kern / 1e6, st["format_bytes"] / kern / 1e6))
         print("upload+format wall %.3f s, preprocess %.4f s (%s)" % (t_up, st["preprocess_seconds"], "GPU" if a.gpu_format else "host"))
         print(st)
+    elif a.range:
+        for _ in range(64):
+            ctx.spmv()
+        ctx.profiler(True)
+        for _ in range(a.range):
+            ctx.spmv()
+        ctx.profiler(False)
+        print("range: %d SpMVs, algorithmic bytes %d, format bytes %d per SpMV" % (a.range, st["algorithmic_bytes"], st["format_bytes"]))
     else:
         for _ in range(a.spmv):
             ctx.spmv()
