@@ -199,6 +199,24 @@ struct FixedArith {                                   // ap_ufixed<32,8,AP_RND,A
         *p = 0ull;
         return (a >> 32) ? 0xFFFFFFFFu : (uint32_t)a;                              // AP_SAT (pe.h:72)
     }
+    // four consecutive rows (row % 4 == 0) for drain_rows: raw accumulator words, their re-zeroing, the result words
+    struct Raw4 { ulonglong2 a, b; };
+    static __device__ __forceinline__ Raw4 load4(const void *acc, uint32_t row) {
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(reinterpret_cast<const unsigned long long *>(acc) + row);
+        Raw4 r;
+        r.a = __ldcg(p);
+        r.b = __ldcg(p + 1);
+        return r;
+    }
+    static __device__ __forceinline__ void zero4(void *acc, uint32_t row, bool stream) {
+        ulonglong2 *p = reinterpret_cast<ulonglong2 *>(reinterpret_cast<unsigned long long *>(acc) + row);
+        const ulonglong2 z = make_ulonglong2(0ull, 0ull);
+        if (stream) { __stcs(p, z); __stcs(p + 1, z); } else { p[0] = z; p[1] = z; }
+    }
+    static __device__ __forceinline__ uint4 final4(const Raw4 &r) {
+        auto sat = [](unsigned long long a) { return (a >> 32) ? 0xFFFFFFFFu : (uint32_t)a; };    // AP_SAT (pe.h:72)
+        return make_uint4(sat(r.a.x), sat(r.a.y), sat(r.b.x), sat(r.b.y));
+    }
 };
 struct FloatArith {                                   // fp32 multiply, then fp32 add (not fused)
     typedef float acc_t;
@@ -230,7 +248,73 @@ struct FloatArith {                                   // fp32 multiply, then fp3
         *p = 0.0f;
         return __float_as_uint(a);
     }
+    typedef uint4 Raw4;
+    static __device__ __forceinline__ Raw4 load4(const void *acc, uint32_t row) {
+        return __ldcg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(acc) + row));
+    }
+    static __device__ __forceinline__ void zero4(void *acc, uint32_t row, bool stream) {
+        uint4 *p = reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(acc) + row);
+        if (stream) __stcs(p, make_uint4(0u, 0u, 0u, 0u)); else *p = make_uint4(0u, 0u, 0u, 0u);
+    }
+    static __device__ __forceinline__ uint4 final4(const Raw4 &r) { return r; }
 };
+
+// The result drain proper (pe dump + result_packer + axis_merge + spmv_result_drain of the reference, pe.h:95-116,
+// spmv_cluster.h:133-193, stream_utils.h:36-75, spmv_result_drain.cpp:36-113, and the PE's reset loop pe.h:131-135):
+// y[r] = clamp(acc[r]); acc[r] = 0 for r in [begin, end), by `n_threads` threads of which this is `t`. The result
+// words also go to the mapped host buffer of a deferred download and to the gathered vectors of the target ranks.
+// Four rows per 128-bit access and kDrainUnroll independent accesses in flight per thread: with one 4-byte load
+// per thread and iteration the drain of a 12.5 M-row shard was latency bound at 0.4 TB/s and took 580 us of a
+// 1.42 ms SpMV. `stream` (launches whose accumulator buffers exceed the L2, sync_start): the re-zeroing stores
+// and y are written with the streaming (evict-first) policy, so that the drained buffer stops competing for the
+// L2 with the live one.
+constexpr int kDrainUnroll = 4;
+template <class A>
+__device__ __forceinline__ void drain_rows(void *acc, uint32_t *y, uint32_t begin, uint32_t end, uint32_t *y_host,
+                                           uint32_t y_host_rows, const GatherTargets *gt, bool stream, uint32_t t,
+                                           uint32_t n_threads) {
+    const int n_targets = gt ? gt->n : 0;
+    auto one = [&](uint32_t r) {
+        const uint32_t v = A::drain(acc, r);
+        y[r] = v;
+        if (y_host && r < y_host_rows) __stcs(y_host + r, v);          // posted write over PCIe
+        for (int g = 0; g < n_targets; g++) gt->y[g][r] = v;           // NVLink peer stores
+    };
+    // 16-byte accesses need 4-aligned rows in every destination: the buffers themselves are 256-byte aligned
+    // (cudaMalloc), a gather target starts at this rank's row offset
+    bool vec = (reinterpret_cast<uintptr_t>(y_host) & 15u) == 0;       // (a caller's host buffer may start anywhere)
+    for (int g = 0; g < n_targets; g++) vec &= (reinterpret_cast<uintptr_t>(gt->y[g]) & 15u) == 0;
+    const uint32_t b4 = vec ? min(end, (begin + 3u) & ~3u) : end;
+    const uint32_t e4 = b4 + ((end - b4) & ~3u);
+    for (uint32_t r = begin + t; r < b4; r += n_threads) one(r);
+    for (uint32_t r = e4 + t; r < end; r += n_threads) one(r);
+    const uint32_t n_chunks = (e4 - b4) >> 2;
+    for (uint32_t c0 = t; c0 < n_chunks; c0 += n_threads * kDrainUnroll) {
+        typename A::Raw4 raw[kDrainUnroll];
+#pragma unroll
+        for (int u = 0; u < kDrainUnroll; u++) {
+            const uint32_t c = c0 + u * n_threads;
+            if (c < n_chunks) raw[u] = A::load4(acc, b4 + 4u * c);
+        }
+#pragma unroll
+        for (int u = 0; u < kDrainUnroll; u++) {
+            const uint32_t c = c0 + u * n_threads;
+            if (c >= n_chunks) break;
+            const uint32_t r = b4 + 4u * c;
+            A::zero4(acc, r, stream);
+            const uint4 v = A::final4(raw[u]);
+            if (stream) __stcs(reinterpret_cast<uint4 *>(y + r), v); else *reinterpret_cast<uint4 *>(y + r) = v;
+            if (y_host) {
+                if (r + 4u <= y_host_rows) __stcs(reinterpret_cast<uint4 *>(y_host + r), v);
+                else {
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                    for (uint32_t k = 0; k < 4u && r + k < y_host_rows; k++) __stcs(y_host + r + k, w[k]);
+                }
+            }
+            for (int g = 0; g < n_targets; g++) *reinterpret_cast<uint4 *>(gt->y[g] + r) = v;
+        }
+    }
+}
 
 // The CTA's dynamic shared memory: xs[0..7] = 0 (padding slots), xs[8 + c] = x[tile column c].
 extern __shared__ __align__(128) uint32_t xs[];
@@ -540,13 +624,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
             __syncwarp();
         }
         const GatherTargets *gt = p.gather;
-        const int n_targets = gt ? gt->n : 0;
-        for (uint32_t r = p.drain_begin + blockIdx.x * kThreads + tid; r < p.drain_end; r += gridDim.x * kThreads) {
-            const uint32_t v = A::drain(p.drain_acc, r);
-            p.y[r] = v;
-            if (p.y_host && r < p.y_host_rows) __stcs(p.y_host + r, v);        // posted write over PCIe
-            for (int g = 0; g < n_targets; g++) gt->y[g][r] = v;               // NVLink peer stores, coalesced
-        }
+        drain_rows<A>(p.drain_acc, p.y, p.drain_begin, p.drain_end, p.y_host, p.y_host_rows, gt, HSB_L2_HINTS && p.sync_start,
+                      blockIdx.x * kThreads + tid, gridDim.x * kThreads);
         if (blockIdx.x == 0 && tid == 0) (void)A::drain(p.drain_acc, p.trash_row);
         if (gt) gather_publish(gt, p.gather_seq);
     }
@@ -567,12 +646,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
 template <class A>
 __global__ void drain_kernel(void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end, uint32_t trash_row,
                              const GatherTargets *gt, uint32_t gather_seq) {
-    const int n_targets = gt ? gt->n : 0;
-    for (uint32_t r = row_begin + blockIdx.x * blockDim.x + threadIdx.x; r < row_end; r += gridDim.x * blockDim.x) {
-        const uint32_t v = A::drain(acc, r);
-        y[r] = v;
-        for (int g = 0; g < n_targets; g++) gt->y[g][r] = v;
-    }
+    drain_rows<A>(acc, y, row_begin, row_end, nullptr, 0u, gt, false, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     if (blockIdx.x == 0 && threadIdx.x == 0) (void)A::drain(acc, trash_row);
     if (gt) gather_publish(gt, gather_seq);
 }

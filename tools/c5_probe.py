@@ -49,8 +49,9 @@ def main():
     ctx.spmv()
     y = ctx.download_result()
     step_ms, _ = ctx.time_spmv(2, args.steps, kernel=False)
+    _, isolated_ms = ctx.time_spmv(1, args.steps, kernel=True)      # an event pair around every launch: no overlap between launches
     out = {"rows": args.rows, "cols": args.cols, "nnz": int(m.nnz), "impl": args.impl, "generate_s": t_gen,
-           "format_s": t_fmt, "ms_per_spmv": step_ms, "gops": 2.0 * m.nnz / step_ms / 1e6,
+           "format_s": t_fmt, "ms_per_spmv": step_ms, "ms_isolated_launch": isolated_ms, "gops": 2.0 * m.nnz / step_ms / 1e6,
            "alg_gbs": st["algorithmic_bytes"] / step_ms / 1e6, "format_gbs": st["format_bytes"] / step_ms / 1e6,
            "format_bytes_per_nnz": st["format_bytes"] / max(m.nnz, 1), "n_col_tiles": st["n_col_tiles"],
            "tile_cols": st["tile_cols"], "n_streams": st["n_streams"], "n_slices": st["n_slices"],
