@@ -343,6 +343,26 @@ __device__ __forceinline__ void mac4(A &acc, uint32_t xs_base, const uint4 &v, c
     acc.mac(v.w, gather_hi(xs_base, c.y));
 }
 
+// The accumulator buffer of this launch was last used four launches ago and re-zeroed by the drain at the end of
+// launch seq-3. In the steady state that launch is long gone; the guard only ever spins when several small
+// launches are resident at once. Every warp checks for itself, before it waits for the x tile (so the poll
+// overlaps the staging and nobody waits for anybody else's poll): lane 0 polls with acquire loads at GPU scope
+// (the flag is a release store of an earlier launch on this GPU), the warp-wide shuffle orders the other lanes'
+// row updates behind it. Launches with two buffers in rotation wait for their predecessor instead (sync_start).
+// false: the wait timed out -- the caller makes no row update and the host hears of it.
+__device__ __forceinline__ bool accumulators_ready(const SpmvParams &p, uint32_t lane) {
+    if (p.sync_start) asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint32_t ok = 1u;
+    if (p.guard_flag) {
+        if (lane == 0) {
+            ok = (p.acquire ? wait_flag_geq<kAcqGpu>(p.guard_flag, p.guard_val) : wait_flag_geq<kAcqNone>(p.guard_flag, p.guard_val)) ? 1u : 0u;
+            if (!ok) atomicExch(p.error_flag, 1u);
+        }
+        ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
+    }
+    return ok != 0u;
+}
+
 // Slice geometry of a tile from its 32-entry table (lane c holds cnt_ge[c], see TileDesc):
 // first step of tile-relative slice i, and the balancing weight (steps + one unit per slice).
 __device__ __forceinline__ uint32_t steps_before(uint32_t cnt, uint32_t i) {
@@ -390,11 +410,12 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, uint64_t *bar,
             if (sl + 1 + a < n_slices) row_next[a] = __ldg(rp + (1 + a) * kLanes);
     }
 
-    // x tile staged AND (first segment) the accumulator buffer is ours: thread 0 arrives on the barrier a
-    // second time once it has seen the guard flag, see the kernel
+    // (first segment) the accumulator buffer must be ours before the first row update: every warp checks the
+    // guard itself, while the x tile is still on its way (see the kernel)
+    const bool guard_ok = !first_segment || accumulators_ready(p, lane);
     mbar_wait(bar, parity);
     if (p.timeline && first_segment && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[(size_t)(p.seq & 255u) * 8 + 4] = globaltimer();
-    if (!remaining || *abort_flag) return;                  // a flag wait timed out: no row update from stale data
+    if (!remaining || !guard_ok || *abort_flag) return;     // a flag wait timed out: no row update from stale data
 
     uint32_t xs_base = smem_u32(xs);
     asm volatile("" : "+r"(xs_base));                        // keep it in a register: no per-step rematerialisation
@@ -475,9 +496,10 @@ __device__ __forceinline__ void stream_units_narrow(const SpmvParams &p, uint64_
     vp += kNarrowRing * kUnitElems;
     cp += kNarrowRing * kUnitElems;
 
+    const bool guard_ok = !first_segment || accumulators_ready(p, lane);
     mbar_wait(bar, parity);
     if (p.timeline && first_segment && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[(size_t)(p.seq & 255u) * 8 + 4] = globaltimer();
-    if (!remaining || *abort_flag) return;
+    if (!remaining || !guard_ok || *abort_flag) return;
 
     uint32_t xs_base = smem_u32(xs);
     asm volatile("" : "+r"(xs_base));
@@ -548,20 +570,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
     // %globaltimer timeline.)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    // The accumulator buffer of this launch was last used four launches ago and re-zeroed by the drain at
-    // the end of launch seq-3. In the steady state that launch is long gone; the guard only ever spins when
-    // several small launches are resident at once. ONE thread checks it (acquire), after it has issued the x
-    // copies, and only then arrives on the CTA's barrier a second time: every warp's first row update is
-    // ordered behind the barrier, hence behind the guard, and the poll overlaps the x staging.
-    auto guard = [&]() -> bool {
-        if (p.sync_start) asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (p.guard_flag && !(p.acquire ? wait_flag_geq<kAcqGpu>(p.guard_flag, p.guard_val) : wait_flag_geq<kAcqNone>(p.guard_flag, p.guard_val))) return false;
-        return true;
-    };
-
     if (g0 < g1) {
         if (tid == 0) {
-            mbar_init(&bar, 2);                                   // arrive.expect_tx (x bytes) + arrive (guard passed)
+            mbar_init(&bar, 1);                                   // arrive.expect_tx: the x tile's bytes
             abort_flag = 0u;
         }
         if (tid < kColBias) xs[tid] = 0u;                         // what padding slots multiply by
@@ -580,6 +591,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
                     // the vector was written through the generic proxy (peer SM stores) or by the copy engine;
                     // the bulk copy below reads it through the async proxy
                     if (p.acquire) asm volatile("fence.proxy.async.global;" ::: "memory");
+                    if (!ok) {                                 // timed out: nobody multiplies the stale vector, the host hears of it
+                        abort_flag = 1u;
+                        atomicExch(p.error_flag, 1u);
+                    }
                 }
                 if (tl && blockIdx.x == 0 && g == g0) tl[1] = globaltimer();
                 fence_proxy_async();
@@ -595,12 +610,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
                     bulk_g2s(smem_raw + kXTileOffset + off, src + off, min(kBulkPiece, bytes - off), &bar);
                     k = k + 1 == pieces ? 0 : k + 1;
                 }
-                if (g == g0) ok &= guard();
-                if (!ok) {                                     // timed out: nobody multiplies, the host hears of it
-                    abort_flag = 1u;
-                    atomicExch(p.error_flag, 1u);
-                }
-                mbar_arrive(&bar);
             }
             // this warp's equal-cost share of the segment (host plan)
             const uint32_t ta = __ldg(&sg->warp_t[warp]), tb = __ldg(&sg->warp_t[warp + 1]);

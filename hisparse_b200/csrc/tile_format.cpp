@@ -29,13 +29,14 @@ uint32_t choose_tile_cols(uint32_t cols, uint32_t rows, uint64_t nnz) {
     // narrower tiles, because the x staging of a tile sits on every CTA's critical path (C2: 2 tiles of
     // 54 K columns 16.6 us, 3-4 tiles 15.1-15.2 us): at most 44,000 columns when rows still have a few
     // entries per tile (longer lane streams, fewer row updates: C4 65.2 -> 62.5 us against 32,768), at most
-    // 32,768 for hypersparse matrices with less than one entry per (row, tile), where wider tiles only make
-    // the staging longer (C5 shard: 1.43 ms at 32 K, 1.81 ms at 56 K).
+    // the full 57,344 for hypersparse matrices with less than one entry per (row, tile): these use the narrow
+    // layout, where fewer, wider tiles mean fewer lane streams and fewer per-tile start-ups (C5 shard, narrow
+    // layout: 0.894 ms at 32 K, 0.874 at 44 K, 0.815 at 56 K; the wide layout had preferred 32 K).
     uint32_t cap = kMaxTileCols;
     if (cols > kMaxTileCols) {
         const uint64_t tiles44 = (cols + 44000u - 1) / 44000u;
         const double per_row_tile = rows ? (double)nnz / ((double)rows * (double)tiles44) : 0.0;
-        cap = per_row_tile >= 1.0 ? 44000u : 32768u;
+        cap = per_row_tile >= 1.0 ? 44000u : kMaxTileCols;
     }
     if (const char *e = std::getenv("HSB_TILE_COLS")) {          // tuning aid
         uint32_t v = (uint32_t)std::atoi(e) & ~7u;

@@ -118,7 +118,7 @@ inline size_t slice_elem(size_t base, int lane, uint32_t k) {
 bool choose_narrow(uint64_t nnz, uint64_t n_segments);
 
 // Choose a tile width (multiple of 8, widths equalised): one tile when x fits shared memory, otherwise tiles
-// of at most 44,000 columns, or 32,768 for hypersparse matrices (less than one entry per row and tile).
+// of at most 44,000 columns, or the full 57,344 for hypersparse matrices (less than one entry per row and tile).
 uint32_t choose_tile_cols(uint32_t cols, uint32_t rows, uint64_t nnz);
 
 // CSR (32-bit value words, passed through untouched) -> tile streams. rows_per_part == 0 means

@@ -212,8 +212,8 @@ int main(void) {
 
 
 def test_tile_width_rule():
-    """one tile while x fits shared memory; <= 44,000 columns for ordinary wide matrices; <= 32,768 when there is
-    less than one entry per row and tile (hypersparse)"""
+    """one tile while x fits shared memory; <= 44,000 columns for ordinary wide matrices; up to the full 57,344 when
+    there is less than one entry per row and tile (hypersparse: narrow layout)"""
     q = hsoracle.Port().quantize
     r, c, ip, ix, d = matgen.random_csr(256, 57344, 0.002, 1)
     assert capi.Format(r, c, ip, ix, q(d)).stats()["n_col_tiles"] == 1
@@ -222,7 +222,7 @@ def test_tile_width_rule():
     assert st["n_col_tiles"] == 3 and st["tile_cols"] <= 44000
     r, c, ip, ix, d = matgen.random_csr(4000, 400000, 0.000005, 3)             # ~2 entries per row over 10+ tiles
     st = capi.Format(r, c, ip, ix, q(d)).stats()
-    assert st["n_col_tiles"] == 13 and st["tile_cols"] <= 32768
+    assert st["n_col_tiles"] == 7 and st["tile_cols"] <= 57344 and st["layout"] == 1
 
 
 # ------------------------------------------------------------------------------------------
