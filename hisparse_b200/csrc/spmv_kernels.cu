@@ -282,7 +282,10 @@ __device__ __forceinline__ void drain_rows(void *acc, uint32_t *y, uint32_t begi
     };
     // 16-byte accesses need 4-aligned rows in every destination: the buffers themselves are 256-byte aligned
     // (cudaMalloc), a gather target starts at this rank's row offset
-    bool vec = (reinterpret_cast<uintptr_t>(y_host) & 15u) == 0;       // (a caller's host buffer may start anywhere)
+    // ... and only pay off when a thread has several rows to drain: with at most one row per thread the scalar
+    // loop keeps every SM busy and is the shorter path on the completion chain of small launches (C1, C3: +0.5 us
+    // per SpMV with the vector loop; C2 with host buffers 18.3 -> 22.5 us, its posted writes coming from 26 SMs only)
+    bool vec = end - begin > n_threads && (reinterpret_cast<uintptr_t>(y_host) & 15u) == 0;
     for (int g = 0; g < n_targets; g++) vec &= (reinterpret_cast<uintptr_t>(gt->y[g]) & 15u) == 0;
     const uint32_t b4 = vec ? min(end, (begin + 3u) & ~3u) : end;
     const uint32_t e4 = b4 + ((end - b4) & ~3u);
@@ -412,7 +415,7 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, uint64_t *bar,
 
     // (first segment) the accumulator buffer must be ours before the first row update: every warp checks the
     // guard itself, while the x tile is still on its way (see the kernel)
-    const bool guard_ok = !first_segment || accumulators_ready(p, lane);
+    const bool guard_ok = !first_segment || !remaining || accumulators_ready(p, lane);   // (warps without work make no row update)
     mbar_wait(bar, parity);
     if (p.timeline && first_segment && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[(size_t)(p.seq & 255u) * 8 + 4] = globaltimer();
     if (!remaining || !guard_ok || *abort_flag) return;     // a flag wait timed out: no row update from stale data
@@ -496,7 +499,7 @@ __device__ __forceinline__ void stream_units_narrow(const SpmvParams &p, uint64_
     vp += kNarrowRing * kUnitElems;
     cp += kNarrowRing * kUnitElems;
 
-    const bool guard_ok = !first_segment || accumulators_ready(p, lane);
+    const bool guard_ok = !first_segment || !remaining || accumulators_ready(p, lane);   // (warps without work make no row update)
     mbar_wait(bar, parity);
     if (p.timeline && first_segment && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[(size_t)(p.seq & 255u) * 8 + 4] = globaltimer();
     if (!remaining || !guard_ok || *abort_flag) return;
