@@ -491,11 +491,14 @@ __device__ __forceinline__ void stream_units_narrow(const SpmvParams &p, uint64_
     const uint16_t *cp = p.cols + base;
     uint32_t vb[kNarrowRing], cb[kNarrowRing];
 #pragma unroll
-    for (int j = 0; j < kNarrowRing; j++)
+    for (int j = 0; j < kNarrowRing; j++) {
+        vb[j] = 0u;
+        cb[j] = 0u;                                            // (slots beyond the share: a valid id for the look-ahead gather)
         if ((uint32_t)j < remaining) {
             vb[j] = ldg_stream32(vp + j * kUnitElems);
             cb[j] = ldg_stream16(cp + j * kUnitElems);
         }
+    }
     vp += kNarrowRing * kUnitElems;
     cp += kNarrowRing * kUnitElems;
 
@@ -509,14 +512,19 @@ __device__ __forceinline__ void stream_units_narrow(const SpmvParams &p, uint64_
     A acc;
     acc.clear();
     uint32_t sl = first_slice, left = 0, row = 0;
-    auto consume = [&](uint32_t v, uint32_t c) {
+    // x word of a column id; a row unit's ids are 0 and fetch the zero word in front of the tile, so the gather
+    // can be issued for EVERY unit, one unit ahead of its use, before it is known what kind of unit it is
+    auto gather = [&](uint32_t c) {
+        uint32_t xv;
+        asm volatile("{\n\t.reg .u32 t;\n\tmad.lo.u32 t, %1, 4, %2;\n\tld.shared.u32 %0, [t];\n\t}" : "=r"(xv) : "r"(c), "r"(xs_base));
+        return xv;
+    };
+    auto consume = [&](uint32_t v, uint32_t xv) {
         if (left == 0) {                                       // warp-uniform: a row unit opens slice sl
             row = v;
             left = steps_of(cnt, sl);
             return;
         }
-        uint32_t xv;
-        asm("{\n\t.reg .u32 t;\n\tmad.lo.u32 t, %1, 4, %2;\n\tld.shared.u32 %0, [t];\n\t}" : "=r"(xv) : "r"(c), "r"(xs_base));
         acc.mac(v, xv);
         if (--left == 0) {                                     // the slice is complete: one row update per lane stream
             typename A::acc_t t = acc.total();
@@ -530,15 +538,19 @@ __device__ __forceinline__ void stream_units_narrow(const SpmvParams &p, uint64_
             sl++;
         }
     };
+    uint32_t xv_next = gather(cb[0]);
     while (remaining >= (uint32_t)kNarrowRing) {
 #pragma unroll
         for (int j = 0; j < kNarrowRing; j++) {
-            const uint32_t v = vb[j], c = cb[j];
+            const uint32_t v = vb[j], xv = xv_next;
             if (remaining > (uint32_t)(kNarrowRing + j)) {
                 vb[j] = ldg_stream32(vp + j * kUnitElems);
                 cb[j] = ldg_stream16(cp + j * kUnitElems);
             }
-            consume(v, c);
+            // the next unit sits in slot j + 1, or (j + 1 == ring size) in slot 0, reloaded at the top of this round;
+            // when nothing follows the slot is stale and the word fetched is simply not used
+            xv_next = gather(cb[(j + 1) % kNarrowRing]);
+            consume(v, xv);
         }
         vp += kNarrowRing * kUnitElems;
         cp += kNarrowRing * kUnitElems;
@@ -546,7 +558,11 @@ __device__ __forceinline__ void stream_units_narrow(const SpmvParams &p, uint64_
     }
 #pragma unroll
     for (int j = 0; j < kNarrowRing - 1; j++)
-        if ((uint32_t)j < remaining) consume(vb[j], cb[j]);
+        if ((uint32_t)j < remaining) {
+            const uint32_t xv = xv_next;
+            xv_next = gather(cb[j + 1]);
+            consume(vb[j], xv);
+        }
 }
 
 // kNarrow selects the layout at compile time: the two streaming loops live in separate kernels, so that each gets
