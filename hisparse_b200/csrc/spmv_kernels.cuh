@@ -60,7 +60,7 @@ constexpr int kPrefetch = HSB_PREFETCH;              // slice steps in flight pe
 #endif
 constexpr int kRowAhead = HSB_ROW_AHEAD;             // slices whose row ids are loaded ahead of their use
 #ifndef HSB_NARROW_RING
-#define HSB_NARROW_RING 10
+#define HSB_NARROW_RING 12
 #endif
 constexpr int kNarrowRing = HSB_NARROW_RING;         // narrow layout: units (192 B per warp) in flight per warp
 
