@@ -822,3 +822,17 @@ def test_narrow_layout_float(gpu, port, monkeypatch):
     y = ctx.download_result()
     ctx.close()
     check_float(y, port, indptr, indices, data, x)
+
+
+@pytest.mark.parametrize("impl", ["fixed", "float_pob"])
+def test_cpp_multi_gpu_driver_single_rank(gpu, impl):
+    """hisparse_b200/host/benchmark_mgpu.cpp with a world of one (the N-GPU runs are `benchmark_mgpu_* <spec> N` on an
+    N-GPU box): NCCL communicator, broadcast of x into the engine, gather connect, gathered y checked on the host."""
+    import subprocess
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hisparse_b200", "host")
+    subprocess.run(["make", "-s", "-C", host], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(host, "bin", "benchmark_mgpu_" + impl), "rmat:20000:400000:3", "1"], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "matches the host reference of the whole matrix" in r.stdout and "GOPS }" in r.stdout
+    assert "===== Benchmark Finished =====" in r.stdout

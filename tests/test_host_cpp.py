@@ -103,3 +103,38 @@ def test_csim_harness_binaries_call_the_library():
     if capi.device_count() == 0:
         r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
         assert r.returncode != 0 and "top_wrapper on the GPU failed" in r.stderr
+
+
+def test_cpp_sharding_matches_python(tmp_path):
+    """hisparse_b200/host/sharding.h (the C++ multi-GPU driver's row-block cut) == hisparse_b200/sharding.py"""
+    from hisparse_b200 import sharding
+    rows, cols, indptr, indices, data = matgen.rmat_csr(5000, 90000, 23)
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
+    src = tmp_path / "shard.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <cstdlib>
+#include "sharding.h"
+int main(int argc, char **argv) {
+    std::vector<uint32_t> ip;
+    for (unsigned v; std::scanf("%u", &v) == 1;) ip.push_back(v);
+    for (int world = 1; world <= 5; world++) {
+        for (uint32_t b : spmv::shard::shard_bounds(ip, world)) std::printf("%u ", b);
+        std::printf("\n");
+    }
+    spmv::io::CSRMatrix<float> m;
+    m.num_rows = (uint32_t)ip.size() - 1; m.num_cols = 8; m.adj_indptr = ip;
+    m.adj_indices.assign(ip.back(), 1u); m.adj_data.assign(ip.back(), 2.0f);
+    auto s = spmv::shard::extract_shard(m, 128, 384);
+    std::printf("%u %u %u %zu\n", s.num_rows, s.adj_indptr.front(), s.adj_indptr.back(), s.adj_indices.size());
+    return 0;
+}
+''')
+    exe = tmp_path / "shard"
+    subprocess.run(["g++", "-O1", "-std=c++14", "-I", HOST, str(src), "-o", str(exe), "-lz"], check=True)
+    out = subprocess.run([str(exe)], input=" ".join(str(int(v)) for v in ip2), capture_output=True, text=True,
+                         check=True).stdout.splitlines()
+    for world in range(1, 6):
+        assert [int(v) for v in out[world - 1].split()] == sharding.shard_bounds(ip2, world)
+    n = int(ip2[384]) - int(ip2[128])
+    assert [int(v) for v in out[5].split()] == [256, 0, n, n]
