@@ -670,9 +670,12 @@ int hsb_upload_matrix_csr(hsb_ctx *c, uint32_t rows, uint32_t cols, const uint32
     return upload_tiled(c, M);
 }
 
-int hsb_upload_matrix_csr_device(hsb_ctx *c, uint32_t rows, uint32_t cols, uint64_t nnz, const uint32_t *d_indptr,
-                                 const uint32_t *d_indices, const void *d_vals, uint32_t rows_per_partition) {
-    if (!c || !d_indptr || (nnz && (!d_indices || !d_vals))) return set_err(HSB_EINVAL, "null argument");
+}  // extern "C"
+
+namespace {
+// device-resident CSR (d_indptr) or COO (d_coo_rows) -> tile streams on the device -> resident matrix
+int upload_device_matrix(hsb_ctx *c, uint32_t rows, uint32_t cols, uint64_t nnz, const uint32_t *d_indptr, const uint32_t *d_coo_rows,
+                         const uint32_t *d_indices, const void *d_vals, uint32_t rows_per_partition) {
     CUDA_TRY(cudaSetDevice(c->device));
     { int rc = quiesce(c); if (rc) return rc; }
     auto t0 = std::chrono::steady_clock::now();
@@ -680,12 +683,12 @@ int hsb_upload_matrix_csr_device(hsb_ctx *c, uint32_t rows, uint32_t cols, uint6
     hsb::TiledMatrix M;
     hsb::DeviceFormat f;
     std::string err;
-    cudaError_t e = hsb::build_tiled_gpu(rows, cols, nnz, d_indptr, d_indices, (const uint32_t *)d_vals,
+    cudaError_t e = hsb::build_tiled_gpu(rows, cols, nnz, d_indptr, d_coo_rows, d_indices, (const uint32_t *)d_vals,
                                          rows_per_partition, hsb::choose_tile_cols(cols, rows, nnz), c->stream, &M, &f, &err);
     if (e != cudaSuccess) {
         cudaFree(f.vals); cudaFree(f.cols); cudaFree(f.slice_rows);
         cudaGetLastError();
-        if (!err.empty()) return set_err(HSB_EINVAL, "malformed CSR: " + err);
+        if (!err.empty()) return set_err(HSB_EINVAL, "malformed matrix: " + err);
         return set_err(HSB_ECUDA, std::string("GPU formatting failed: ") + cudaGetErrorString(e));
     }
     c->preprocess_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -695,6 +698,15 @@ int hsb_upload_matrix_csr_device(hsb_ctx *c, uint32_t rows, uint32_t cols, uint6
         CUDA_TRY(cudaMalloc(&d.vals, 16)); CUDA_TRY(cudaMalloc(&d.cols, 16)); CUDA_TRY(cudaMalloc(&d.slice_rows, 16));
     }
     return install_matrix(c, M, d, f.n_elems, f.n_slices);
+}
+}  // namespace
+
+extern "C" {
+
+int hsb_upload_matrix_csr_device(hsb_ctx *c, uint32_t rows, uint32_t cols, uint64_t nnz, const uint32_t *d_indptr,
+                                 const uint32_t *d_indices, const void *d_vals, uint32_t rows_per_partition) {
+    if (!c || !d_indptr || (nnz && (!d_indices || !d_vals))) return set_err(HSB_EINVAL, "null argument");
+    return upload_device_matrix(c, rows, cols, nnz, d_indptr, nullptr, d_indices, d_vals, rows_per_partition);
 }
 
 int hsb_upload_matrix_csr_gpu(hsb_ctx *c, uint32_t rows, uint32_t cols, const uint32_t *indptr,
@@ -735,18 +747,18 @@ int hsb_upload_matrix_cpsr(hsb_ctx *c, const void *const ch[HSB_NUM_HBM_CHANNELS
     if (!host_format) {
         // the channel images go to HBM as they are; decoding and re-formatting run on the device
         CUDA_TRY(cudaSetDevice(c->device));
-        uint32_t *d_ip = nullptr, *d_ix = nullptr, *d_v = nullptr;
+        uint32_t *d_rows = nullptr, *d_ix = nullptr, *d_v = nullptr;     // a COO list in image order
         uint64_t nnz = 0;
         std::string derr;
         cudaError_t e = hsb::cpsr_decode_gpu(c->cfg, imgs, ch_packets, num_row_partitions, num_col_partitions, num_rows,
-                                             num_cols, c->stream, &d_ip, &d_ix, &d_v, &nnz, &derr);
+                                             num_cols, c->stream, &d_rows, &d_ix, &d_v, &nnz, &derr);
         if (e != cudaSuccess) {
             cudaGetLastError();
             if (!derr.empty()) return set_err(HSB_EINVAL, "malformed CPSR image: " + derr);
             return set_err(HSB_ECUDA, std::string("GPU decoding failed: ") + cudaGetErrorString(e));
         }
-        int rc = hsb_upload_matrix_csr_device(c, num_rows, num_cols, nnz, d_ip, d_ix, d_v, c->cfg.ob_size);
-        cudaFree(d_ip); cudaFree(d_ix); cudaFree(d_v);
+        int rc = upload_device_matrix(c, num_rows, num_cols, nnz, nullptr, d_rows, d_ix, d_v, c->cfg.ob_size);
+        cudaFree(d_rows); cudaFree(d_ix); cudaFree(d_v);
         c->preprocess_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         return rc;
     }

@@ -43,10 +43,11 @@ bool cpsr_decode(const ImplConfig &cfg, const uint32_t *const images[16], const 
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 namespace hsb {
-// The same decoding done on the GPU (cpsr_decode_gpu.cu): host images in, device CSR out (caller frees).
+// The same decoding done on the GPU (cpsr_decode_gpu.cu): host images in, device COO list (row, column, value per
+// non-zero, image order) out (caller frees).
 cudaError_t cpsr_decode_gpu(const ImplConfig &cfg, const uint32_t *const images[16], const size_t n_packets[16],
                             uint32_t num_row_partitions, uint32_t num_col_partitions, uint32_t num_rows,
-                            uint32_t num_cols, cudaStream_t stream, uint32_t **d_indptr, uint32_t **d_indices,
+                            uint32_t num_cols, cudaStream_t stream, uint32_t **d_rows, uint32_t **d_cols,
                             uint32_t **d_vals, uint64_t *nnz, std::string *err);
 }  // namespace hsb
 #endif

@@ -39,17 +39,23 @@ struct StreamRec {
 
 __device__ __forceinline__ uint32_t n_pieces(uint32_t n, uint32_t max_len) { return (n + max_len - 1) / max_len; }
 
-// one thread per non-zero: key = ((part * T + tile) << 32) | row
-__global__ void k_keys(uint64_t nnz, uint32_t rows, const uint32_t *__restrict__ indptr,
+// one thread per non-zero: key = ((part * T + tile) << 32) | row; the row comes from the CSR row pointers, or
+// (coo_rows != null) from a COO list
+__global__ void k_keys(uint64_t nnz, uint32_t rows, const uint32_t *__restrict__ indptr, const uint32_t *__restrict__ coo_rows,
                        const uint32_t *__restrict__ indices, uint32_t rows_per_part, uint32_t tile_cols,
                        uint32_t T, uint32_t cols, unsigned long long *__restrict__ keys, uint32_t *__restrict__ ids,
                        int *__restrict__ bad) {
     uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nnz) return;
     uint32_t lo = 0, hi = rows;                       // last row r with indptr[r] <= e
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (indptr[mid] <= e) lo = mid; else hi = mid;
+    if (coo_rows) {
+        lo = coo_rows[e];
+        if (lo >= rows) { *bad = 1; keys[e] = 0; ids[e] = (uint32_t)e; return; }
+    } else {
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (indptr[mid] <= e) lo = mid; else hi = mid;
+        }
     }
     const uint32_t col = indices[e];
     if (col >= cols) { *bad = 1; keys[e] = 0; ids[e] = (uint32_t)e; return; }
@@ -184,7 +190,7 @@ inline int bits_for(uint64_t v) { int b = 0; while ((1ull << b) <= v && b < 63) 
 
 }  // namespace
 
-cudaError_t build_tiled_gpu(uint32_t rows, uint32_t cols, uint64_t nnz, const uint32_t *d_indptr,
+cudaError_t build_tiled_gpu(uint32_t rows, uint32_t cols, uint64_t nnz, const uint32_t *d_indptr, const uint32_t *d_coo_rows,
                             const uint32_t *d_indices, const uint32_t *d_vals, uint32_t rows_per_part,
                             uint32_t tile_cols, cudaStream_t stream, TiledMatrix *meta, DeviceFormat *out,
                             std::string *err) {
@@ -236,7 +242,7 @@ cudaError_t build_tiled_gpu(uint32_t rows, uint32_t cols, uint64_t nnz, const ui
     GF_TRY(sc.get(&ids, nnz)); GF_TRY(sc.get(&ids_s, nnz));
     GF_TRY(sc.get(&bad, 1));
     GF_TRY(cudaMemsetAsync(bad, 0, sizeof(int), stream));
-    k_keys<<<blocks(nnz), TB, 0, stream>>>(nnz, rows, d_indptr, d_indices, M.rows_per_part, tile_cols, T, cols, keys, ids, bad);
+    k_keys<<<blocks(nnz), TB, 0, stream>>>(nnz, rows, d_indptr, d_coo_rows, d_indices, M.rows_per_part, tile_cols, T, cols, keys, ids, bad);
     const int key_bits = 32 + bits_for(NT);
     size_t need = 0;
     GF_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys_s, ids, ids_s, (int)nnz, 0, key_bits, stream));
@@ -255,7 +261,7 @@ cudaError_t build_tiled_gpu(uint32_t rows, uint32_t cols, uint64_t nnz, const ui
     uint32_t n_segs = 0;
     GF_TRY(cudaMemcpyAsync(&n_segs, d_nsegs, 4, cudaMemcpyDeviceToHost, stream));
     GF_TRY(cudaStreamSynchronize(stream));
-    if (h_bad) return fail("column index out of range");
+    if (h_bad) return fail("row or column index out of range");
 
     // layout (tile_format.h): narrow when the segments are nearly all one or two entries long
     M.narrow = choose_narrow(nnz, n_segs);

@@ -48,6 +48,9 @@ static spmv::io::CSRMatrix<float> load(const std::string &spec) {
     return m;
 }
 
+static int g_device = 0;
+static int runtime_device(hsb_runtime &) { return g_device; }
+
 benchmark_result spmv_benchmark(hsb_runtime &runtime, spmv::io::CSRMatrix<float> &ext_matrix) {
     using namespace spmv::io;
     using namespace std::chrono;
@@ -91,6 +94,30 @@ benchmark_result spmv_benchmark(hsb_runtime &runtime, spmv::io::CSRMatrix<float>
     std::cout << "INFO : with host buffers (x up, y down per SpMV): " << e2e_s * 1e3 << " ms pipelined ("
               << 2.0 * nnz / 1e9 / e2e_s << " GOPS), " << e2e_sync_s * 1e3 << " ms synchronous ("
               << 2.0 * nnz / 1e9 / e2e_sync_s << " GOPS)" << std::endl;
+    // The reference's own route into the accelerator: csr2cpsr + the 16 channel packet images on the host
+    // (sw/host.cpp:147-231, what paper Table 8 times), then the images are handed over unchanged and decoded /
+    // re-formatted on the GPU (hsb_upload_matrix_cpsr). Skipped for matrices beyond the U280's 16 x 256 MB.
+    if (st.nnz <= 200u * 1000u * 1000u && std::getenv("HSB_BENCH_SKIP_CPSR") == nullptr) {
+        auto h0 = high_resolution_clock::now();
+        const size_t nrp = (mat.num_rows + LOGICAL_OB_SIZE - 1) / LOGICAL_OB_SIZE, ncp = (mat.num_cols + LOGICAL_VB_SIZE - 1) / LOGICAL_VB_SIZE;
+        CPSRMatrix<PACKED_VAL_T, PACKED_IDX_T, PACK_SIZE> cpsr = csr2cpsr<PACKED_VAL_T, PACKED_IDX_T, VAL_T, IDX_T, PACK_SIZE>(
+            mat, IDX_MARKER, LOGICAL_OB_SIZE, LOGICAL_VB_SIZE, NUM_HBM_CHANNELS * INTERLEAVE_FACTOR, true);
+        std::vector<std::vector<SPMV_MAT_PKT_T> > images = build_channel_images<SPMV_MAT_PKT_T>(cpsr, NUM_HBM_CHANNELS, INTERLEAVE_FACTOR);
+        const double host_s = duration<double>(high_resolution_clock::now() - h0).count();
+        const void *ch[NUM_HBM_CHANNELS];
+        size_t ch_packets[NUM_HBM_CHANNELS], bytes = 0;
+        for (size_t c = 0; c < NUM_HBM_CHANNELS; c++) { ch[c] = images[c].data(); ch_packets[c] = images[c].size(); bytes += images[c].size() * 64; }
+        hsb_runtime second(runtime_device(runtime), HSB_IMPL);
+        auto g0 = high_resolution_clock::now();
+        HSB_CHECK(hsb_upload_matrix_cpsr(second.ctx, ch, ch_packets, (unsigned)nrp, (unsigned)ncp, mat.num_rows, mat.num_cols));
+        const double gpu_s = duration<double>(high_resolution_clock::now() - g0).count();
+        hsb_stats s2;
+        HSB_CHECK(hsb_get_stats(second.ctx, &s2));
+        std::cout << "INFO : CPSR route: csr2cpsr + channel images on the host " << host_s << " s (" << bytes / 1e6 << " MB of packets); "
+                  << "images -> resident tile streams on the GPU " << gpu_s << " s (copy + decode + format; nnz " << s2.nnz
+                  << (s2.nnz == st.nnz ? ", same matrix" : ", MISMATCH") << "), against " << r.preprocess_time_s << " s from the CSR" << std::endl;
+        if (s2.nnz != st.nnz) exit(EXIT_FAILURE);
+    }
     return r;
 }
 
@@ -99,7 +126,8 @@ int main(int argc, char **argv) {
         std::cout << "Usage: " << argv[0] << " <dataset.npz | dense:R:C | uniform:R:C:K | random:R:C:NNZ:SEED | rmat:N:EDGES:SEED> [device]" << std::endl;
         return 0;
     }
-    hsb_runtime runtime(argc > 2 ? atoi(argv[2]) : 0, HSB_IMPL);
+    g_device = argc > 2 ? atoi(argv[2]) : 0;
+    hsb_runtime runtime(g_device, HSB_IMPL);
     std::string dataset = argv[1];
     std::cout << "------ Running benchmark on " << dataset << std::endl;
     spmv::io::CSRMatrix<float> mat_f = load(dataset);

@@ -836,3 +836,32 @@ def test_cpp_multi_gpu_driver_single_rank(gpu, impl):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "matches the host reference of the whole matrix" in r.stdout and "GOPS }" in r.stdout
     assert "===== Benchmark Finished =====" in r.stdout
+
+
+def test_cpsr_ingestion_googleplus_size(gpu, port):
+    """The reference's channel images of the C2-sized matrix (131 MB of 64-byte packets, 4 column partitions) handed
+    over unchanged: decoded by one warp per lane-stream piece and formatted on the device. Bit-exact SpMV, and the
+    whole upload (copy + decode + format) stays within a small multiple of the CSR route's time."""
+    import time
+    rows, cols, indptr, indices, data = matgen.rmat_csr(107614, 13_670_000, 0xC0FFEE02)
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
+    words = port.quantize((data * np.float32(0.05)).astype(np.float32))
+    cfg = capi.get_config(capi.IMPL_FIXED)
+    m = port.csr2cpsr(r2, c2, ip2, indices, words, 8, cfg.logical_ob_size, cfg.logical_vb_size, 16, True, hsoracle.VAL_Q824)
+    images = m.channel_images(1)
+    xw = port.quantize(np.random.default_rng(8).random(c2, dtype=np.float32))
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)            # warm-up of the formatter's allocations + the CSR time
+    t0 = time.perf_counter()
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+    t_csr = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ctx.upload_matrix_cpsr(images, m.n_row_parts, m.n_col_parts, r2, c2)
+    t_cpsr = time.perf_counter() - t0
+    assert ctx.stats()["nnz"] == indices.size
+    ctx.upload_vector(xw)
+    ctx.spmv()
+    assert np.array_equal(ctx.download_result(), port.spmv_q824(ip2, indices, words, xw))
+    ctx.close()
+    print("CPSR images -> resident: %.1f ms; CSR -> resident: %.1f ms" % (1e3 * t_cpsr, 1e3 * t_csr))
+    assert t_cpsr < 4 * t_csr + 0.05
