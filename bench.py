@@ -234,6 +234,24 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<u4", "data": (ptr, False), "version": 2}
 
 
+def pin_to_gpu_node(capi, device):
+    """Run this rank's host thread on the CPUs of the NUMA node its GPU hangs off (sysfs), so that the per-SpMV
+    uploads and downloads of N ranks do not all cross one socket; the page-locked buffers themselves are already
+    allocated on that node (hsb_host_alloc). Silently keeps the inherited affinity when the platform does not say."""
+    node = capi.lib().hsb_device_numa_node(device)
+    try:
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node, len(cpus)
+    except (OSError, ValueError):
+        return node, 0
+
+
 def _max_over_ranks(dist, dev, *vals):
     import torch
     t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
@@ -485,6 +503,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from hisparse_b200 import matgen
+    if world > 1:
+        pin_to_gpu_node(capi, local)
     L2_BYTES = capi.device_l2_bytes(local) or L2_BYTES
     impl = WORKLOADS[WORKLOAD][1]
     ctx = capi.Context(local, impl)

@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include <sched.h>
 #include <sys/syscall.h>
 #include <unistd.h>
 
@@ -793,10 +794,18 @@ int hsb_upload_vector(hsb_ctx *c, const void *x_packed, unsigned num_cols) {
         if (need) {
             if (need > c->publish_sure) { int rc = publish_done(c); if (rc) return rc; }
             const auto t0 = std::chrono::steady_clock::now();
-            for (unsigned spins = 0; (int32_t)(*c->h_done - need) < 0; spins++)
-                if ((spins & 0xFFFu) == 0xFFFu &&
-                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0)
-                    return set_err(HSB_ECUDA, "timed out waiting for the launch that still reads the x buffer");
+            // bounded back-off: a pause per poll (the mapped word is written over PCIe; hammering it from several
+            // ranks' host threads on one socket slows everybody's posted writes), a yield every 64 K polls
+            for (unsigned spins = 0; (int32_t)(*c->h_done - need) < 0; spins++) {
+#if defined(__x86_64__) || defined(__i386__)
+                __builtin_ia32_pause();
+#endif
+                if ((spins & 0xFFFFu) == 0xFFFFu) {
+                    sched_yield();
+                    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0)
+                        return set_err(HSB_ECUDA, "timed out waiting for the launch that still reads the x buffer");
+                }
+            }
         }
         cudaStream_t up = (c->x_seq & 1u) ? c->s_h2d_b : c->s_h2d;
         CUDA_TRY(cudaMemcpyAsync(c->d_x[b], x_packed, (size_t)num_cols * 4, cudaMemcpyHostToDevice, up));
