@@ -117,7 +117,8 @@ struct hsb_ctx {
     hsb::Segment *d_segs = nullptr;
     std::vector<uint32_t> plan_grid;      // CTAs used by each of those launches
     std::vector<uint32_t> plan_steps, plan_slices;   // slot 0: steps / slices started per CTA (profiling aid)
-    uint32_t smem_bytes = 0;              // dynamic shared memory a launch needs: widest x tile + the zero words
+    uint32_t smem_bytes = 0;              // dynamic shared memory a launch needs: widest x tile + the zero words (+ combining tables)
+    uint32_t comb_offset = 0;             // where the combining tables start in it, or 0: none
     // vectors
     // x is multi-buffered so that the upload of the next vector (copy stream) overlaps the SpMV that still
     // reads the current one; x_words words each (padded to whole tiles, zero filled). Event mode rotates two
@@ -321,6 +322,10 @@ int install_matrix(hsb_ctx *c, const hsb::TiledMatrix &M, const DeviceMatrix &d,
     uint32_t widest = 8;
     for (const auto &td : M.tiles) widest = std::max(widest, td.col_count);
     c->smem_bytes = widest * 4u + hsb::kXTileOffset;
+    // the two combining tables of the wide kernel (Segment::comb_n) go behind the x tile when the CTA has room
+    c->comb_offset = 0;
+    const uint32_t comb_bytes = 2u * hsb::kCombineSlots * hsb::kLanes * (uint32_t)esz, at = (c->smem_bytes + 15u) & ~15u;
+    if (!M.narrow && at + comb_bytes <= hsb::kSmemBytes) { c->comb_offset = at; c->smem_bytes = at + comb_bytes; }
     c->next_replica = 0;
     c->have_matrix = true;
     return HSB_OK;
@@ -471,6 +476,7 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
     p.drain_acc = c->drain_pending ? c->d_acc[(c->acc_cur + c->acc_bufs - 1) % c->acc_bufs] : nullptr;
     p.acquire = c->acquire ? 1u : 0u;
     p.narrow = c->meta.narrow ? 1u : 0u;
+    p.comb_offset = c->comb_offset;
     if (c->d_gather && c->drain_pending) { p.gather = c->d_gather; p.gather_seq = ++c->gather_seq; }
     p.drain_begin = c->drain_begin; p.drain_end = c->drain_end;
     p.trash_row = c->rows;

@@ -187,6 +187,7 @@ struct FixedArith {                                   // ap_ufixed<32,8,AP_RND,A
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
         return v;
     }
+    static __device__ __forceinline__ void add_shared(acc_t *slot, acc_t v) { if (v) atomicAdd(slot, v); }
     // alpha (*) y (+) beta with the PE's product rounding / saturation (pe.h:64) and saturating add (pe.h:72)
     static __device__ __forceinline__ uint32_t axpb(uint32_t alpha, uint32_t y, uint32_t beta) {
         unsigned long long q = ((unsigned long long)alpha * y + 0x800000ull) >> 24;
@@ -239,6 +240,7 @@ struct FloatArith {                                   // fp32 multiply, then fp3
         for (int d = 16; d > 0; d >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
         return v;
     }
+    static __device__ __forceinline__ void add_shared(acc_t *slot, acc_t v) { atomicAdd(slot, v); }
     static __device__ __forceinline__ uint32_t axpb(uint32_t alpha, uint32_t y, uint32_t beta) {
         return __float_as_uint(__fadd_rn(__fmul_rn(__uint_as_float(alpha), __uint_as_float(y)), __uint_as_float(beta)));
     }
@@ -378,10 +380,11 @@ __device__ __forceinline__ uint32_t steps_of(uint32_t cnt, uint32_t i) {
 // columns) steps that may start and end inside a slice. Lanes own lane streams; whenever a slice
 // (or the run) ends, the lane's partial sum is added to its row and the accumulator restarts.
 template <class A>
-__device__ __forceinline__ void stream_steps(const SpmvParams &p, uint64_t *bar, uint32_t parity,
+__device__ __forceinline__ bool stream_steps(const SpmvParams &p, uint64_t *bar, uint32_t parity,
                                              uint32_t cnt, uint32_t slice_begin, uint32_t n_slices,
                                              uint32_t step_begin, uint32_t ta, uint32_t tb, uint32_t first_slice,
-                                             uint32_t lane, bool first_segment, const volatile uint32_t *abort_flag) {
+                                             uint32_t lane, bool first_segment, const volatile uint32_t *abort_flag,
+                                             typename A::acc_t *comb, uint32_t comb_first, bool comb_drainer) {
     uint32_t remaining = tb - ta;
     const size_t base = (size_t)(step_begin + ta) * kStepElems;
     const uint4 *vp = reinterpret_cast<const uint4 *>(p.vals + base) + lane;
@@ -415,10 +418,12 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, uint64_t *bar,
 
     // (first segment) the accumulator buffer must be ours before the first row update: every warp checks the
     // guard itself, while the x tile is still on its way (see the kernel)
-    const bool guard_ok = !first_segment || !remaining || accumulators_ready(p, lane);   // (warps without work make no row update)
+    // (warps without work -- and without a share of the combining table to flush -- make no row update)
+    const bool guard_ok = !first_segment || !(remaining || comb_drainer) || accumulators_ready(p, lane);
     mbar_wait(bar, parity);
     if (p.timeline && first_segment && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[(size_t)(p.seq & 255u) * 8 + 4] = globaltimer();
-    if (!remaining || !guard_ok || *abort_flag) return;     // a flag wait timed out: no row update from stale data
+    if (!guard_ok) return false;
+    if (!remaining || *abort_flag) return true;             // a flag wait timed out: no row update from stale data
 
     uint32_t xs_base = smem_u32(xs);
     asm volatile("" : "+r"(xs_base));                        // keep it in a register: no per-step rematerialisation
@@ -429,6 +434,10 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, uint64_t *bar,
     // same-address atomics (which the L2 would serialise).
     auto flush = [&]() {
         typename A::acc_t v = acc.total();
+        if (comb) {                                          // combined in shared memory, flushed once per segment (see the kernel)
+            A::add_shared(comb + (sl - comb_first) * kLanes + lane, v);
+            return;
+        }
         if (__all_sync(0xFFFFFFFFu, row == __shfl_sync(0xFFFFFFFFu, row, 0))) {
             v = A::warp_sum(v);
             if (lane == 0) A::emit(p.acc, row, v);
@@ -473,6 +482,7 @@ __device__ __forceinline__ void stream_steps(const SpmvParams &p, uint64_t *bar,
         }
     // the run ended inside a slice: hand over what has been accumulated so far
     if (left != steps_of(cnt, sl) && sl < n_slices) flush();
+    return true;
 }
 
 // Narrow layout (hypersparse matrices, tile_format.h): one warp streams units [ta, tb) of a tile, 32 elements
@@ -595,6 +605,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
             abort_flag = 0u;
         }
         if (tid < kColBias) xs[tid] = 0u;                         // what padding slots multiply by
+        typedef typename A::acc_t acc_t;
+        acc_t *comb_base = (!kNarrow && p.comb_offset) ? reinterpret_cast<acc_t *>(smem_raw + p.comb_offset) : nullptr;
+        if (comb_base)
+            for (uint32_t i = tid; i < 2u * kCombineSlots * kLanes; i += kThreads) comb_base[i] = acc_t(0);
         __syncthreads();
         uint32_t parity = 0;
         for (uint32_t g = g0; g < g1; g++) {
@@ -633,11 +647,33 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
             // this warp's equal-cost share of the segment (host plan)
             const uint32_t ta = __ldg(&sg->warp_t[warp]), tb = __ldg(&sg->warp_t[warp + 1]);
             const uint32_t first_slice = __ldg(&sg->warp_slice[warp]);
+            // Row updates of a segment that touches only a few slices are combined in shared memory first: the warps
+            // that share a slice (the pruned transformer layers: one or two 32-step slices per CTA, split over 32
+            // warps) add their partial sums into a table, and the table goes to the row accumulators once, after the
+            // barrier -- 32 x fewer global row updates, all of which would hit the same few rows. Two tables alternate
+            // by segment, so the flush of one overlaps the next segment's work.
+            const uint32_t comb_first = __ldg(&sg->comb_first), comb_n = comb_base ? __ldg(&sg->comb_n) : 0u;
+            acc_t *comb = comb_n ? comb_base + ((g - g0) & 1u) * (kCombineSlots * kLanes) : nullptr;
+            bool ok = true;
             if (kNarrow) stream_units_narrow<A>(p, &bar, parity, cnt, h1.w, ta, tb, first_slice, lane, g == g0, &abort_flag);
-            else stream_steps<A>(p, &bar, parity, cnt, h1.y, h1.z, h1.w, ta, tb, first_slice, lane, g == g0, &abort_flag);
+            else ok = stream_steps<A>(p, &bar, parity, cnt, h1.y, h1.z, h1.w, ta, tb, first_slice, lane, g == g0, &abort_flag,
+                                      comb, comb_first, warp < comb_n);
             parity ^= 1u;
             if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * (kWarps + 2) + warp] = clock64() - t_start;
             __syncthreads();                                       // everyone is done with this x tile
+            if (comb)
+                for (uint32_t s = warp; s < comb_n; s += kWarps) {
+                    const acc_t v = comb[s * kLanes + lane];
+                    comb[s * kLanes + lane] = acc_t(0);
+                    if (!ok || abort_flag) continue;               // (a timed-out wait: no row update, the host hears of it)
+                    const uint32_t row = __ldg(p.slice_rows + (size_t)(h1.y + comb_first + s) * kLanes + lane);
+                    if (__all_sync(0xFFFFFFFFu, row == __shfl_sync(0xFFFFFFFFu, row, 0))) {
+                        const acc_t t = A::warp_sum(v);
+                        if (lane == 0) A::emit(p.acc, row, t);
+                    } else {
+                        A::emit(p.acc, row, v);
+                    }
+                }
         }
     }
     if (tl && blockIdx.x == 0 && tid == 0) tl[6] = globaltimer();

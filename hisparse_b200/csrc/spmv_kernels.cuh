@@ -46,7 +46,8 @@ constexpr int kWarps = kWarpsPerCta;                 // one CTA per SM
 constexpr int kThreads = kWarps * 32;
 constexpr uint32_t kXTileBytes = kMaxTileCols * 4;   // 224 KB
 constexpr uint32_t kXTileOffset = kColBias * 4;      // xs[0..7] = 0: what padding slots (column id 0) gather
-constexpr uint32_t kSmemBytes = kXTileBytes + kXTileOffset;   // upper bound; a launch asks for what its tiles need
+constexpr uint32_t kSmemBytes = 232448;              // 227 KB: the most a CTA can opt in to; a launch asks for what its tiles need
+                                                     // (x tile + the zero words + the combining tables when they fit)
 #ifndef HSB_BULK_PIECE
 #define HSB_BULK_PIECE 16384
 #endif
@@ -105,6 +106,8 @@ struct SpmvParams {
     const struct GatherTargets *gather;   // device-resident table, or null
     uint32_t gather_seq;          // value the arrival flags receive: gathered drains so far, this one included
     uint32_t acquire;             // 1: flag waits are acquire loads (+ fence.proxy.async before the x TMA)
+    uint32_t comb_offset;         // byte offset (from the start of dynamic shared memory) of the two row-update combining
+                                  // tables, kCombineSlots x 32 accumulators each (Segment::comb_n), or 0: no room, no combining
     uint32_t narrow;              // 1: the matrix is in the narrow layout (tile_format.h): units of 32 elements, a row
                                   // unit in front of every slice, shares cut at slice boundaries; slice_rows unused
 };

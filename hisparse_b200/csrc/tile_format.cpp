@@ -426,6 +426,12 @@ Segment make_segment(const TiledMatrix &m, uint32_t tile, uint32_t t_lo, uint32_
     std::memcpy(g.cnt_ge, td.cnt_ge, sizeof g.cnt_ge);
     const double c0 = cost_at_step(m, td, t_lo), c1 = cost_at_step(m, td, t_hi);
     const uint32_t total = tile_steps_total(m, td);
+    if (t_hi > t_lo && t_lo < total) {
+        g.comb_first = slice_of_step_host(m, td, t_lo);
+        const uint32_t span = slice_of_step_host(m, td, t_hi - 1) - g.comb_first + 1;
+        static const bool combine = [] { const char *e = std::getenv("HSB_COMBINE"); return !e || std::atoi(e) != 0; }();   // A/B aid
+        g.comb_n = (!m.narrow && combine && span <= kCombineSlots) ? span : 0u;
+    }
     for (int w = 0; w <= kWarpsPerCta; w++) {
         uint32_t t = w == 0 ? t_lo : (w == kWarpsPerCta ? t_hi : step_at_cost(m, td, c0 + (c1 - c0) * w / (double)kWarpsPerCta));
         t = std::min(std::max(t, w ? g.warp_t[w - 1] : t_lo), t_hi);

@@ -139,8 +139,15 @@ struct Segment {
     // [warp_t[w], warp_t[w+1]) and starts inside tile-relative slice warp_slice[w]
     uint32_t warp_t[33];
     uint32_t warp_slice[32];
-    uint32_t pad_[3];
+    // In-CTA combining of row updates (wide layout): when the segment touches at most kCombineSlots slices, a slice
+    // is usually split over several warps (the pruned transformer layers: 32-step slices, one or two per CTA), and
+    // every warp would send its own 32 partial sums to the same few rows. The warps then add their partial sums
+    // into a shared-memory table indexed by (slice - comb_first, lane) and the table is flushed once per segment.
+    uint32_t comb_first;     // tile-relative index of the first slice the segment touches
+    uint32_t comb_n;         // slices it touches if <= kCombineSlots, else 0 (no combining)
+    uint32_t pad_[1];
 };
+constexpr uint32_t kCombineSlots = 48;
 static_assert(sizeof(Segment) % 16 == 0, "Segment is loaded with 128-bit loads");
 // Work plan for one launch over tiles [tile_begin, tile_end) on `ctas` CTAs: CTA b runs
 // segs[cta_seg[b] .. cta_seg[b+1]). Cuts are placed at equal cost (steps + one unit per slice,

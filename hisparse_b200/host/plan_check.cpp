@@ -79,6 +79,8 @@ static int walk_plan_fixed(const hsb::TiledMatrix &M, uint32_t ctas, const uint3
                 const size_t base = (size_t)(sg.step_begin + ta) * hsb::kStepElems;
                 unsigned long long lane_acc[hsb::kLanes] = {};
                 auto flush = [&]() {
+                    // (the kernel's shared-memory combining table covers slices [comb_first, comb_first + comb_n))
+                    if (sg.comb_n && (sl < sg.comb_first || sl - sg.comb_first >= sg.comb_n)) return false;
                     for (int l = 0; l < hsb::kLanes; l++) {
                         const uint32_t row = M.slice_rows[(size_t)(sg.slice_begin + sl) * hsb::kLanes + l];
                         if (row > M.rows) return false;
