@@ -46,7 +46,7 @@ constexpr int kWarps = kWarpsPerCta;                 // one CTA per SM
 constexpr int kThreads = kWarps * 32;
 constexpr uint32_t kXTileBytes = kMaxTileCols * 4;   // 224 KB
 constexpr uint32_t kXTileOffset = kColBias * 4;      // xs[0..7] = 0: what padding slots (column id 0) gather
-constexpr uint32_t kSmemBytes = 232448;              // 227 KB: the most a CTA can opt in to; a launch asks for what its tiles need
+constexpr uint32_t kSmemBytes = 232448 - 256;        // 227 KB (the most a CTA can opt in to) less the static variables; a launch asks for what its tiles need
                                                      // (x tile + the zero words + the combining tables when they fit)
 #ifndef HSB_BULK_PIECE
 #define HSB_BULK_PIECE 16384
