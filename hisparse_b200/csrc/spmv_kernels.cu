@@ -529,16 +529,19 @@ __device__ __forceinline__ void stream_units_narrow(const SpmvParams &p, uint64_
         asm volatile("{\n\t.reg .u32 t;\n\tmad.lo.u32 t, %1, 4, %2;\n\tld.shared.u32 %0, [t];\n\t}" : "=r"(xv) : "r"(c), "r"(xs_base));
         return xv;
     };
+    bool full_len = false;                                     // the current slice has the maximum length: maybe pieces of ONE long row
     auto consume = [&](uint32_t v, uint32_t xv) {
         if (left == 0) {                                       // warp-uniform: a row unit opens slice sl
             row = v;
             left = steps_of(cnt, sl);
+            full_len = left == kNarrowMaxLen;
             return;
         }
         acc.mac(v, xv);
         if (--left == 0) {                                     // the slice is complete: one row update per lane stream
             typename A::acc_t t = acc.total();
-            if (__all_sync(0xFFFFFFFFu, row == __shfl_sync(0xFFFFFFFFu, row, 0))) {
+            // (a row cut into 32-entry streams fills whole slices of the maximum length: only those can be one row)
+            if (full_len && __all_sync(0xFFFFFFFFu, row == __shfl_sync(0xFFFFFFFFu, row, 0))) {
                 t = A::warp_sum(t);
                 if (lane == 0) A::emit(p.acc, row, t);
             } else {
@@ -549,6 +552,20 @@ __device__ __forceinline__ void stream_units_narrow(const SpmvParams &p, uint64_
         }
     };
     uint32_t xv_next = gather(cb[0]);
+    // bulk of the share: every slot consumed is refilled, no per-unit bounds test
+    while (remaining >= 2u * (uint32_t)kNarrowRing) {
+#pragma unroll
+        for (int j = 0; j < kNarrowRing; j++) {
+            const uint32_t v = vb[j], xv = xv_next;
+            vb[j] = ldg_stream32(vp + j * kUnitElems);
+            cb[j] = ldg_stream16(cp + j * kUnitElems);
+            xv_next = gather(cb[(j + 1) % kNarrowRing]);
+            consume(v, xv);
+        }
+        vp += kNarrowRing * kUnitElems;
+        cp += kNarrowRing * kUnitElems;
+        remaining -= kNarrowRing;
+    }
     while (remaining >= (uint32_t)kNarrowRing) {
 #pragma unroll
         for (int j = 0; j < kNarrowRing; j++) {
