@@ -503,8 +503,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from hisparse_b200 import matgen
+    placement = None
     if world > 1:
-        pin_to_gpu_node(capi, local)
+        placement = pin_to_gpu_node(capi, local)
     L2_BYTES = capi.device_l2_bytes(local) or L2_BYTES
     impl = WORKLOADS[WORKLOAD][1]
     ctx = capi.Context(local, impl)
@@ -729,6 +730,10 @@ def main():
             "preprocess_s": st["preprocess_seconds"],
         }
         out["config"]["parity"] = parity
+        if placement is not None:
+            out["config"]["host_placement"] = {"rank0_gpu_numa_node": placement[0], "rank0_cpus_pinned": placement[1],
+                                               "what": "every rank's host thread runs on the CPUs of its GPU's NUMA node (sysfs); "
+                                                       "page-locked buffers are allocated on that node (hsb_host_alloc)"}
         if sharded is not None:
             out["sharded"] = sharded
         if world == 1 and not args.no_cpu_baseline:
