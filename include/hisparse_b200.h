@@ -207,7 +207,9 @@ int hsb_time_e2e(hsb_ctx *ctx, const void *const x_host[2], void *const y_host[2
  * stream memory operations), 0 = stream events between launches; "xwait_once": 1 = launches stop polling
  * the x flag once one that polled it has completed (default); "host_drain": 1 = deferred downloads into
  * page-locked memory are written by the kernel's drain itself instead of the copy engine (default); "acquire":
- * 1 = the kernels' flag waits end in fence.acq_rel.sys + fence.proxy.async (default), 0 = relaxed (A/B aid). */
+ * 1 = the kernels' flag waits are acquire loads + fence.proxy.async (default), 0 = relaxed (A/B aid); "xflag_copy":
+ * 1 = the "vector has landed" flag is written by a 4-byte copy behind the vector's copy (default), 0 = by a stream
+ * memory operation. */
 int hsb_set_option(hsb_ctx *ctx, const char *name, int value);
 /* Profiling aid: SM-clock stamps of the last launch, [sm_count][34] = per warp "my slices are done",
  * then CTA "finished" (wait for the predecessor and drain included); the last word is unused. out == NULL arms (capacity != 0) or

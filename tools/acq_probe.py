@@ -27,12 +27,18 @@ py = [capi.PinnedArray(r2) for _ in range(2)]
 for b in px:
     b.array[:] = xw
 xh, yh = [b.array for b in px], [b.array for b in py]
-for acq in (1, 0, 1, 0):
+for acq, xfc in ((1, 1), (1, 0), (1, 1), (1, 0), (0, 1)):
     ctx.set_option("acquire", acq)
+    ctx.set_option("xflag_copy", xfc)
     ctx.upload_vector(xw)
     res = min(ctx.time_spmv(256, 2048, kernel=False)[0] for _ in range(3)) * 1e3
     e2e = min(ctx.time_e2e(xh, yh, 2048, async_download=True) for _ in range(3)) * 1e6
     sync = ctx.time_e2e(xh, yh, 256, async_download=False) * 1e6
-    print("%-24s acquire=%d  resident %.2f us  e2e pipelined %.2f us  synchronous %.2f us"
-          % (os.path.basename(os.environ.get("HSB_LIB", "default")), acq, res, e2e, sync), flush=True)
+    t0 = __import__("time").perf_counter()
+    for k in range(512):
+        ctx.upload_vector(xh[k & 1])
+    ctx.sync()
+    up = (__import__("time").perf_counter() - t0) / 512 * 1e6
+    print("%-24s acquire=%d xflag_copy=%d  resident %.2f us  upload only %.2f us  e2e pipelined %.2f us  synchronous %.2f us"
+          % (os.path.basename(os.environ.get("HSB_LIB", "default")), acq, xfc, res, up, e2e, sync), flush=True)
 ctx.close()
