@@ -142,6 +142,8 @@ struct hsb_ctx {
     int y_cur = 0;                        // THE result vector: every drain writes d_y[y_cur]
     bool y_busy[2] = {false, false};      // an asynchronous download of d_y[b] may still be running
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_h2d_more[2] = {nullptr, nullptr};   // HSB_UPLOAD_STREAMS=3|4: further copy streams in the rotation (A/B aid)
+    int n_upload_streams = 2;
     cudaStream_t s_h2d_b = nullptr;       // flag pipeline: uploads alternate between two streams, so that one copy runs while the other
                                           // stream is still busy with its flag write (a stream memory operation takes ~5 us there)
     cudaEvent_t ev_xready = nullptr, ev_xfree[2] = {nullptr, nullptr}, ev_yready = nullptr, ev_ydone = nullptr;
@@ -545,6 +547,7 @@ int quiesce(hsb_ctx *c) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->s_h2d));
     CUDA_TRY(cudaStreamSynchronize(c->s_h2d_b));
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamSynchronize(c->s_h2d_more[i]));
     CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
     c->y_busy[0] = c->y_busy[1] = false;
     return check_error_flag(c);
@@ -602,6 +605,8 @@ hsb_ctx *hsb_create(int device, int impl) {
     c->sm_count = prop.multiProcessorCount * hsb::kCtasPerSm;    // CTA slots the launch plans are cut for
     e = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_h2d_b, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; i++) if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_h2d_more[i], cudaStreamNonBlocking);
+    if (const char *v = std::getenv("HSB_UPLOAD_STREAMS")) c->n_upload_streams = std::min(4, std::max(1, std::atoi(v)));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
     cudaEvent_t *evs[] = {&c->ev_xready, &c->ev_xfree[0], &c->ev_xfree[1], &c->ev_yready, &c->ev_ydone};
     for (cudaEvent_t *ev : evs)
@@ -641,6 +646,7 @@ void hsb_destroy(hsb_ctx *c) {
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->s_h2d);
     cudaStreamDestroy(c->s_h2d_b);
+    for (int i = 0; i < 2; i++) cudaStreamDestroy(c->s_h2d_more[i]);
     cudaStreamDestroy(c->s_d2h);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -824,7 +830,8 @@ int hsb_upload_vector(hsb_ctx *c, const void *x_packed, unsigned num_cols) {
         // copy-engine operation. A stream memory operation in its place costs 1.7 us more per SpMV in the host-buffer
         // pipeline (C2: 18.8 -> 16.9 us; hsb_set_option "xflag_copy" / HSB_XFLAG_COPY=0 for the A/B). Tried and
         // dropped: the vector as two halves on the two copy streams with two flags (upload 15.2 -> 19.6 us per vector).
-        cudaStream_t up = (c->x_seq & 1u) ? c->s_h2d_b : c->s_h2d;
+        cudaStream_t all_up[4] = {c->s_h2d, c->s_h2d_b, c->s_h2d_more[0], c->s_h2d_more[1]};
+        cudaStream_t up = all_up[c->x_seq % (unsigned)c->n_upload_streams];
         CUDA_TRY(cudaMemcpyAsync(c->d_x[b], x_packed, (size_t)num_cols * 4, cudaMemcpyHostToDevice, up));
         c->x_wait_val = ++c->x_seq;
         c->x_wait_buf = b;
@@ -878,6 +885,7 @@ int hsb_sync(hsb_ctx *c) {
     if (c->have_matrix) { int rc = finish(c); if (rc) return rc; }
     CUDA_TRY(cudaStreamSynchronize(c->s_h2d));
     CUDA_TRY(cudaStreamSynchronize(c->s_h2d_b));
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamSynchronize(c->s_h2d_more[i]));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
     c->y_busy[0] = c->y_busy[1] = false;
@@ -1049,6 +1057,7 @@ int hsb_axpb_to_vector(hsb_ctx *c, uint32_t alpha_word, uint32_t beta_word, uint
     // the buffer being written must not be the target of an upload still in flight
     CUDA_TRY(cudaStreamSynchronize(c->s_h2d));
     CUDA_TRY(cudaStreamSynchronize(c->s_h2d_b));
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamSynchronize(c->s_h2d_more[i]));
     const int nb = c->flags_mode ? kXBuffers : 2;
     const int b = (c->x_latest + 1) % nb;
     const int yb = c->y_cur;
