@@ -274,7 +274,16 @@ int install_matrix(hsb_ctx *c, const hsb::TiledMatrix &M, const DeviceMatrix &d,
     auto plan = [&](size_t slot, uint32_t tile0, uint32_t tile1) {
         uint64_t steps = 0;
         for (uint32_t t = tile0; t < tile1; t++) steps += M.tiles[t].slice_end - M.tiles[t].slice_begin;
-        uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(G, steps));   // >= one slice per CTA
+        // at least kMinSteps steps per CTA (one per warp) when the launch is that small: a tiny launch on a quarter of
+        // the SMs leaves room for its successor to start at once instead of waiting for an SM (HSB_MIN_STEPS_PER_CTA)
+        static const uint64_t min_steps = [] { const char *e = std::getenv("HSB_MIN_STEPS_PER_CTA"); return (uint64_t)std::max(1, e ? std::atoi(e) : 1); }();
+        uint64_t unit_steps = 0;
+        for (uint32_t t = tile0; t < tile1; t++)
+            if (M.tiles[t].slice_end > M.tiles[t].slice_begin) {
+                const hsb::SliceDesc &last = M.slices[M.tiles[t].slice_end - 1];
+                unit_steps += last.off + (last.tile_steps & 0xFFu) - M.tiles[t].step_begin;
+            }
+        uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(G, std::min<uint64_t>(steps, (unit_steps + min_steps - 1) / min_steps)));
         c->plan_grid[slot] = g;
         std::vector<uint32_t> cs;
         hsb::plan_launch(M, tile0, tile1, g, &cs, &segs);
