@@ -57,15 +57,14 @@ def build(force=False):
 
 
 def source_hash():
-    """SHA-256 over the sources libhisparse_b200.so is built from (csrc/ and the public header): identifies a
-    build across recompilations; profiles/traffic.json is keyed by it."""
-    import glob
+    """SHA-256 over the sources that decide what a launch reads from HBM -- the kernels, the format and the
+    planner (csrc/spmv_kernels.*, tile_format.*, gpu_format.cu): identifies a build across recompilations and
+    across changes to the host shim; profiles/traffic.json is keyed by it."""
     import hashlib
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(HERE, "csrc", "*"))) + [HEADER]:
-        if os.path.isfile(f):
-            h.update(os.path.basename(f).encode())
-            h.update(open(f, "rb").read())
+    for name in ("spmv_kernels.cu", "spmv_kernels.cuh", "tile_format.cpp", "tile_format.h", "gpu_format.cu"):
+        h.update(name.encode())
+        h.update(open(os.path.join(HERE, "csrc", name), "rb").read())
     return h.hexdigest()
 
 

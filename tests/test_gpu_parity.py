@@ -865,3 +865,27 @@ def test_cpsr_ingestion_googleplus_size(gpu, port):
     ctx.close()
     print("CPSR images -> resident: %.1f ms; CSR -> resident: %.1f ms" % (1e3 * t_cpsr, 1e3 * t_csr))
     assert t_cpsr < 4 * t_csr + 0.05
+
+
+def test_timed_out_flag_wait_skips_the_row_updates_and_is_reported(gpu, port):
+    """A launch whose x never arrives (here: the slice of a second rank that never sends it) gives up after a bounded
+    wait, makes NO row update, and every way of asking for the result reports the failure -- no hang, no stale y."""
+    r2, c2, ip2, indices, data = _pagerank_matrix(3000, 40000, 51)
+    words = port.quantize(data)
+    alpha, beta = int(port.quantize(np.float32([0.85]))[0]), int(port.quantize(np.float32([0.02]))[0])
+    x0 = port.quantize(np.full(c2, 0.125, np.float32))
+    a, b = capi.Context(0, capi.IMPL_FIXED), capi.Context(0, capi.IMPL_FIXED)
+    for c in (a, b):
+        c.upload_matrix_csr(r2, c2, ip2, indices, words)
+        c.upload_vector(x0)
+    blobs = np.concatenate([a.peer_export(), b.peer_export()])
+    a.peer_connect(2, 0, blobs)
+    b.peer_connect(2, 1, blobs)
+    a.spmv()
+    a.axpb_to_peers(alpha, beta, 0)          # rank 0 sends its slice; rank 1 never does
+    a.vector_commit()
+    a.spmv()                                  # polls two arrival flags, one of which never comes
+    with pytest.raises(capi.HsbError, match="gave up waiting"):
+        a.sync()
+    a.close()
+    b.close()

@@ -313,3 +313,17 @@ def test_both_layouts_round_trip_and_walk(port, monkeypatch, name, make, rpp, ti
     total = sum(r[-1][1] for r in _steps_per_tile(fmt, rec).values())
     assert total * (32 if narrow else 128) == st["n_elems"]
     assert np.array_equal(fmt.emulate_fixed(ctas, x), port.spmv_q824(indptr, indices, words, x))
+
+
+def test_binding_refuses_float64_words():
+    """value / vector arguments are 32-bit words: float64 (scipy's default dtype) must be refused, not truncated;
+    wide integer index arrays are narrowed after a range check"""
+    with pytest.raises(TypeError):
+        capi._words(np.array([0.5, 1.5]))
+    assert capi._words(np.array([1, 2, 3], np.int64)).dtype == np.uint32
+    with pytest.raises(ValueError):
+        capi._words(np.array([1, -2], np.int64))
+    with pytest.raises(ValueError):
+        capi._words(np.array([1 << 33], np.int64))
+    a = np.array([0.5], np.float32)
+    assert capi._words(a).view(np.float32)[0] == np.float32(0.5)
