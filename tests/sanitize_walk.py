@@ -7,7 +7,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this file lives in tests/: it uses the oracle as its checker)
 sys.path.insert(0, ROOT)
 from hisparse_b200 import capi, matgen, sharding  # noqa: E402
 from oracle import hsoracle  # noqa: E402

@@ -8,7 +8,6 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hisparse_b200 import capi, matgen  # noqa: E402
-from oracle import hsoracle  # noqa: E402
 
 
 def make(config):

@@ -3,7 +3,6 @@ import argparse, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hisparse_b200 import capi, matgen  # noqa
-from oracle import hsoracle  # noqa
 from tools.profile_run import make  # noqa
 
 ap = argparse.ArgumentParser(); ap.add_argument("--config", default="c2"); ap.add_argument("--impl", default="fixed")
