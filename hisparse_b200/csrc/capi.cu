@@ -136,6 +136,7 @@ struct hsb_ctx {
     int x_next_buf = -1;                  // buffer hsb_axpb_to_vector wrote and hsb_vector_commit will make current
     bool x_next_from_peers = false;       // ... filled by all ranks (hsb_axpb_to_peers): the next SpMV polls their arrival flags
     bool x_dirty = false;                 // uploaded since the last launch: the launch must wait for the copy
+    bool x_after_grid = false;            // the current x was written by the axpb kernel just in front on the stream: the next launch waits for that grid
     // y is double buffered too: the launch that follows a deferred download drains into d_y[y_cur], the
     // copy engine reads that buffer out, and later launches drain into the other one
     uint32_t *d_y[2] = {nullptr, nullptr}; // rows words each
@@ -492,6 +493,8 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
     p.acquire = c->acquire ? 1u : 0u;
     p.narrow = c->meta.narrow ? 1u : 0u;
     p.comb_offset = c->comb_offset;
+    p.x_after_grid = c->x_after_grid ? 1u : 0u;
+    c->x_after_grid = false;                               // (later launches are ordered behind this one)
     if (c->d_gather && c->drain_pending) { p.gather = c->d_gather; p.gather_seq = ++c->gather_seq; }
     p.drain_begin = c->drain_begin; p.drain_end = c->drain_end;
     p.trash_row = c->rows;
@@ -1104,6 +1107,7 @@ int hsb_vector_commit(hsb_ctx *c) {
     if (!c) return set_err(HSB_EINVAL, "null context");
     if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
     const int nb = c->flags_mode ? kXBuffers : 2;
+    c->x_after_grid = c->x_next_buf >= 0;                 // written by an axpb kernel on the compute stream
     c->x_latest = c->x_next_buf >= 0 ? c->x_next_buf : (c->x_latest + 1) % nb;
     c->x_next_buf = -1;
     c->x_wait_buf = -1;                                    // written on the compute stream: plain stream order

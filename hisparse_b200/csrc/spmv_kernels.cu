@@ -138,9 +138,6 @@ __device__ __forceinline__ bool wait_flag_geq(const uint32_t *flag, uint32_t val
 __device__ __forceinline__ bool wait_flag_geq(const uint32_t *flag, uint32_t val, bool acquire) {
     return acquire ? wait_flag_geq<kAcqSys>(flag, val) : wait_flag_geq<kAcqNone>(flag, val);
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // Grid-wide completion of a drain with a gather epilogue: the CTA that takes the last ticket knows every
 // peer store of this drain has been issued and fenced, and raises this rank's arrival flag on every target.
 __device__ __forceinline__ void gather_publish(const GatherTargets *gt, uint32_t seq) {
@@ -646,6 +643,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
                         atomicExch(p.error_flag, 1u);
                     }
                 }
+                // x was written by the kernel in front of this one on the stream (the axpb step of an iterative caller,
+                // itself a programmatic launch that lets this grid start early): wait for it here, ring already filling
+                if (g == g0 && p.x_after_grid) {
+                    asm volatile("griddepcontrol.wait;" ::: "memory");
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                }
                 if (tl && blockIdx.x == 0 && g == g0) tl[1] = globaltimer();
                 fence_proxy_async();
                 const uint32_t bytes = h1.x * 4u;
@@ -744,6 +747,11 @@ __global__ void wait_flags_kernel(const uint32_t *flags, uint32_t count, uint32_
 template <class A>
 __global__ void axpb_kernel(void *acc, uint32_t *y, uint32_t *x_next, uint32_t rows, uint32_t x_limit, uint32_t alpha,
                             uint32_t beta, uint32_t col_offset, uint32_t trash_row) {
+    // a programmatic dependent launch on both sides: the next SpMV may start (it fills its prefetch ring and then
+    // waits for THIS grid before it stages x), and this grid was allowed to start before the SpMV whose sums it
+    // finalises had retired
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
         uint32_t v;
         if (acc) { v = A::drain(acc, r); y[r] = v; } else { v = y[r]; }
@@ -801,11 +809,18 @@ cudaError_t launch_axpb_peers(int arith, void *acc, uint32_t *y, const PeerTarge
 cudaError_t launch_axpb(int arith, void *acc, uint32_t *y, uint32_t *x_next, uint32_t rows, uint32_t x_limit,
                         uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, cudaStream_t stream) {
     const int grid = (int)std::min<uint32_t>((std::max(rows, 1u) + 255) / 256, (uint32_t)g_sm_count * 8u);
-    if (arith == kArithFixed)
-        axpb_kernel<FixedArith><<<grid, 256, 0, stream>>>(acc, y, x_next, rows, x_limit, alpha, beta, col_offset, trash_row);
-    else
-        axpb_kernel<FloatArith><<<grid, 256, 0, stream>>>(acc, y, x_next, rows, x_limit, alpha, beta, col_offset, trash_row);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    static const bool pdl = std::getenv("HSB_NO_PDL") == nullptr;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (arith == kArithFixed) return cudaLaunchKernelEx(&cfg, axpb_kernel<FixedArith>, acc, y, x_next, rows, x_limit, alpha, beta, col_offset, trash_row);
+    return cudaLaunchKernelEx(&cfg, axpb_kernel<FloatArith>, acc, y, x_next, rows, x_limit, alpha, beta, col_offset, trash_row);
 }
 
 cudaError_t configure_kernels(int sm_count) {

@@ -106,6 +106,8 @@ struct SpmvParams {
     const struct GatherTargets *gather;   // device-resident table, or null
     uint32_t gather_seq;          // value the arrival flags receive: gathered drains so far, this one included
     uint32_t acquire;             // 1: flag waits are acquire loads (+ fence.proxy.async before the x TMA)
+    uint32_t x_after_grid;        // 1: x was written by the kernel in front of this launch on the stream (axpb step): thread 0
+                                  // waits for that grid (griddepcontrol.wait) before it stages the first x tile
     uint32_t comb_offset;         // byte offset (from the start of dynamic shared memory) of the two row-update combining
                                   // tables, kCombineSlots x 32 accumulators each (Segment::comb_n), or 0: no room, no combining
     uint32_t narrow;              // 1: the matrix is in the narrow layout (tile_format.h): units of 32 elements, a row
