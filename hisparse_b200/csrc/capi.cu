@@ -1107,7 +1107,8 @@ int hsb_vector_commit(hsb_ctx *c) {
     if (!c) return set_err(HSB_EINVAL, "null context");
     if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
     const int nb = c->flags_mode ? kXBuffers : 2;
-    c->x_after_grid = c->x_next_buf >= 0;                 // written by an axpb kernel on the compute stream
+    // written by an axpb kernel on the compute stream (the peer form is announced by arrival flags instead, this rank's own slice included)
+    c->x_after_grid = c->x_next_buf >= 0 && !c->x_next_from_peers;
     c->x_latest = c->x_next_buf >= 0 ? c->x_next_buf : (c->x_latest + 1) % nb;
     c->x_next_buf = -1;
     c->x_wait_buf = -1;                                    // written on the compute stream: plain stream order

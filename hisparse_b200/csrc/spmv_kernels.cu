@@ -764,6 +764,10 @@ template <class A>
 __global__ void axpb_peers_kernel(void *acc, uint32_t *y, const PeerTargets t, uint32_t rows, uint32_t x_limit,
                                   uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, uint32_t seq,
                                   uint32_t *ticket) {
+    // programmatic dependent launch on both sides, as axpb_kernel: the next SpMV may start at once -- what it needs
+    // from this grid (and from the other ranks' grids) it learns from the arrival flags it polls before staging x
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
         uint32_t v;
         if (acc) { v = A::drain(acc, r); y[r] = v; } else { v = y[r]; }
@@ -799,11 +803,19 @@ cudaError_t launch_axpb_peers(int arith, void *acc, uint32_t *y, const PeerTarge
                               uint32_t alpha, uint32_t beta, uint32_t col_offset, uint32_t trash_row, uint32_t seq,
                               uint32_t *ticket, cudaStream_t stream) {
     const int grid = (int)std::min<uint32_t>((std::max(rows, 1u) + 255) / 256, (uint32_t)g_sm_count * 4u);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    static const bool pdl = std::getenv("HSB_NO_PDL") == nullptr;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
     if (arith == kArithFixed)
-        axpb_peers_kernel<FixedArith><<<grid, 256, 0, stream>>>(acc, y, t, rows, x_limit, alpha, beta, col_offset, trash_row, seq, ticket);
-    else
-        axpb_peers_kernel<FloatArith><<<grid, 256, 0, stream>>>(acc, y, t, rows, x_limit, alpha, beta, col_offset, trash_row, seq, ticket);
-    return cudaGetLastError();
+        return cudaLaunchKernelEx(&cfg, axpb_peers_kernel<FixedArith>, acc, y, t, rows, x_limit, alpha, beta, col_offset, trash_row, seq, ticket);
+    return cudaLaunchKernelEx(&cfg, axpb_peers_kernel<FloatArith>, acc, y, t, rows, x_limit, alpha, beta, col_offset, trash_row, seq, ticket);
 }
 
 cudaError_t launch_axpb(int arith, void *acc, uint32_t *y, uint32_t *x_next, uint32_t rows, uint32_t x_limit,
