@@ -30,6 +30,12 @@ def main():
     wl = os.environ.get("TL_WORKLOAD", "c2")
     bench.WORKLOAD = wl
     r2, c2, ip2, indices, data, x = bench.workload(0)
+    if os.environ.get("TL_SHARD"):                       # "world:rank": one nnz-balanced row block of the matrix
+        from hisparse_b200 import sharding
+        world, rank = [int(v) for v in os.environ["TL_SHARD"].split(":")]
+        bounds = sharding.shard_bounds(ip2, world)
+        ip2, indices, data = sharding.extract_shard(ip2, indices, data, bounds[rank], bounds[rank + 1])
+        r2 = bounds[rank + 1] - bounds[rank]
     if bench.WORKLOADS[wl][1] == "fixed":
         words, xw = matgen.quantize_q824(data), matgen.quantize_q824(x)
     else:
