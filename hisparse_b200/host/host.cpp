@@ -27,30 +27,31 @@ void compute_ref(spmv::io::CSRMatrix<float> &mat, std::vector<float> &vector, st
             ref_result[r] += mat.adj_data[i] * vector[mat.adj_indices[i]];
 }
 
-bool verify(std::vector<float> reference_results, std::vector<VAL_T> kernel_results) {
-    float epsilon = 0.0001;
-    if (reference_results.size() != kernel_results.size()) {
-        std::cout << "Error: Size mismatch" << std::endl;
-        std::cout << "  Reference result size: " << reference_results.size()
-                  << "  Kernel result size: " << kernel_results.size() << std::endl;
+// The acceptance check of the reference's harness (sw/host.cpp:50-74): every result within 1e-4 (absolute) of the
+// fp32 reference. Own body; the messages keep the reference's wording because scripts grep for them.
+bool verify(const std::vector<float> &reference_results, const std::vector<VAL_T> &kernel_results) {
+    const float epsilon = 0.0001f;
+    const size_t n = reference_results.size();
+    if (kernel_results.size() != n) {
+        std::cout << "Error: Size mismatch" << std::endl
+                  << "  Reference result size: " << n << "  Kernel result size: " << kernel_results.size() << std::endl;
         return false;
     }
-    for (size_t i = 0; i < reference_results.size(); i++) {
-        bool match = std::fabs(float(kernel_results[i]) - reference_results[i]) < epsilon;
-        if (!match) {
-            std::cout << "Error: Result mismatch" << std::endl;
-            std::cout << "  i = " << i << "  Reference result = " << reference_results[i]
-                      << "  Kernel result = " << kernel_results[i] << std::endl;
-            return false;
-        }
-    }
-    return true;
+    size_t first_bad = n;
+    for (size_t i = 0; i < n && first_bad == n; i++)
+        if (!(std::fabs(float(kernel_results[i]) - reference_results[i]) < epsilon)) first_bad = i;     // (NaN fails too)
+    if (first_bad == n) return true;
+    std::cout << "Error: Result mismatch" << std::endl
+              << "  i = " << first_bad << "  Reference result = " << reference_results[first_bad]
+              << "  Kernel result = " << kernel_results[first_bad] << std::endl;
+    return false;
 }
 
-void unpack_vector(aligned_vector<PACKED_VAL_T> &pdv, std::vector<VAL_T> &dv) {
-    dv.resize(pdv.size() * PACK_SIZE);
-    for (size_t i = 0; i < pdv.size(); i++)
-        for (size_t k = 0; k < PACK_SIZE; k++) dv[i * PACK_SIZE + k] = pdv[i].data[k];
+// packed result words (8 per packet, natural row order: sw/host.cpp:76-86) -> one value per row
+void unpack_vector(const aligned_vector<PACKED_VAL_T> &packed, std::vector<VAL_T> &flat) {
+    flat.clear();
+    flat.reserve(packed.size() * PACK_SIZE);
+    for (const PACKED_VAL_T &pkt : packed) flat.insert(flat.end(), pkt.data, pkt.data + PACK_SIZE);
 }
 
 //---------------------------------------------------------------

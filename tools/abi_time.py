@@ -26,6 +26,12 @@ else:
     else:
         words, xw = data.view(np.uint32), x.view(np.uint32)
     np.savez(cache, r2=r2, c2=c2, ip2=ip2, indices=indices, words=words, xw=xw)
+if os.environ.get("ABI_SHARD"):                          # "world:rank": one nnz-balanced row block of the workload
+    from hisparse_b200 import sharding
+    world, rank = [int(v) for v in os.environ["ABI_SHARD"].split(":")]
+    bounds = sharding.shard_bounds(ip2, world)
+    ip2, indices, words = sharding.extract_shard(ip2, indices, words, bounds[rank], bounds[rank + 1])
+    r2 = bounds[rank + 1] - bounds[rank]
 L = C.CDLL(os.environ.get("HSB_LIB") or os.path.join(ROOT, "hisparse_b200", "libhisparse_b200.so"))
 vp, u32 = C.c_void_p, C.c_uint32
 L.hsb_create.restype = vp
