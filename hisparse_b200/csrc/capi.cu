@@ -394,15 +394,21 @@ uint32_t *mapped_alias(hsb_ctx *c, const void *host, size_t n_words) {
     return (uint32_t *)(it->second.dev + (h - it->first));
 }
 
-// a kernel gave up waiting for a flag: report it once (the launch skipped its row updates, y is incomplete)
+// a kernel gave up waiting for a flag: report it once (the launch skipped its row updates, y is incomplete). Callers
+// have synchronised the streams that could still raise it. With the flag pipeline the word is in mapped host memory
+// (h_done[8]): a host load, not the 10 us of a blocking 4-byte copy on every download.
 int check_error_flag(hsb_ctx *c) {
     uint32_t err = 0;
-    CUDA_TRY(cudaMemcpy(&err, c->d_flags + kFlagError, 4, cudaMemcpyDeviceToHost));
-    if (err) {
-        CUDA_TRY(cudaMemset(c->d_flags + kFlagError, 0, 4));
+    if (c->h_done) {
+        err = c->h_done[8];
+        if (err) c->h_done[8] = 0;
+    } else {
+        CUDA_TRY(cudaMemcpy(&err, c->d_flags + kFlagError, 4, cudaMemcpyDeviceToHost));
+        if (err) CUDA_TRY(cudaMemset(c->d_flags + kFlagError, 0, 4));
+    }
+    if (err)
         return set_err(HSB_ECUDA, "a kernel gave up waiting for a flag (vector upload, result download, peer slice or "
                                   "accumulator reuse) and skipped its row updates: the result is incomplete");
-    }
     return HSB_OK;
 }
 
@@ -479,7 +485,7 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
     }
     p.seq = ++c->launch_seq;
     p.done_dev = c->d_flags + kFlagDoneDev;
-    p.error_flag = c->d_flags + kFlagError;
+    p.error_flag = c->d_done ? c->d_done + 8 : c->d_flags + kFlagError;
     if (c->acc_bufs == 2) p.sync_start = 1;
     else if (p.seq > 3) { p.guard_flag = p.done_dev; p.guard_val = p.seq - 3; }
     p.x = c->d_x[c->x_latest]; p.y = c->d_y[yb];
@@ -539,8 +545,16 @@ int finish(hsb_ctx *c) {
             c->y_busy[yb] = false;
         }
         const uint32_t gseq = c->d_gather ? ++c->gather_seq : 0;
+        // a download that was waiting for this drain and goes to mapped page-locked memory rides on it: the drain
+        // kernel writes the result words to the host buffer as well (posted PCIe writes), no copy engine, no event hop
+        uint32_t *y_host = nullptr;
+        uint32_t y_host_rows = 0;
+        if (c->pending_dl.active && c->pending_dl.dev && c->drain_begin == 0 && c->drain_end == c->rows) {
+            y_host = c->pending_dl.dev; y_host_rows = c->pending_dl.n;
+            c->pending_dl.active = false;
+        }
         CUDA_TRY(hsb::launch_drain(c->arith, c->d_acc[(c->acc_cur + c->acc_bufs - 1) % c->acc_bufs], c->d_y[yb], c->drain_begin, c->drain_end, c->rows,
-                                   c->d_gather, gseq, c->stream));
+                                   c->d_gather, gseq, y_host, y_host_rows, c->stream));
         c->launches++;
         c->drain_pending = false;
     }
@@ -928,8 +942,9 @@ int hsb_download_result_async(hsb_ctx *c, void *y_packed, unsigned num_rows) {
 int hsb_download_result(hsb_ctx *c, void *y_packed, unsigned num_rows) {
     int rc = hsb_download_result_async(c, y_packed, num_rows);
     if (rc) return rc;
-    rc = finish(c);                                       // a deferred copy is issued now
-    if (rc) return rc;
+    rc = finish(c);                                       // a deferred download is resolved now: by the drain kernel itself
+    if (rc) return rc;                                    // (mapped page-locked destination) or by the copy engine
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
     c->y_busy[0] = c->y_busy[1] = false;
     return check_error_flag(c);      // a launch that gave up on a flag produced no row updates: never hand that out as y
@@ -1280,7 +1295,7 @@ int hsb_gather_wait(hsb_ctx *c) {
     if (!c->d_gather || !c->gather_is_target) return set_err(HSB_ESTATE, "this rank is not a gather target");
     CUDA_TRY(cudaSetDevice(c->device));
     { int rc = finish(c); if (rc) return rc; }              // this rank's own block of the last SpMV
-    CUDA_TRY(hsb::launch_wait_flags(c->d_gather_flags, (uint32_t)c->gather_world, c->gather_seq, c->d_flags + kFlagError, c->stream));
+    CUDA_TRY(hsb::launch_wait_flags(c->d_gather_flags, (uint32_t)c->gather_world, c->gather_seq, c->d_done ? c->d_done + 8 : c->d_flags + kFlagError, c->stream));
     c->launches++;
     return HSB_OK;
 }

@@ -105,6 +105,11 @@ __device__ __forceinline__ unsigned long long globaltimer() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// a flag wait timed out: every writer stores the same 1, so a plain system-scope store does (the word lives in mapped
+// page-locked host memory when the flag pipeline is on: the host reads it after a stream synchronisation, no copy)
+__device__ __forceinline__ void raise_error(uint32_t *flag) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
+}
 // kAcqNone: relaxed polls. kAcqSys / kAcqGpu: every poll is an acquire load at that scope, so the successful one
 // synchronises with the writer's release (st.release.sys of a peer GPU's kernel, the copy engine's flag write
 // behind its copy, st.release.gpu of an earlier launch): everything the writer did before raising the flag is
@@ -358,7 +363,7 @@ __device__ __forceinline__ bool accumulators_ready(const SpmvParams &p, uint32_t
     if (p.guard_flag) {
         if (lane == 0) {
             ok = (p.acquire ? wait_flag_geq<kAcqGpu>(p.guard_flag, p.guard_val) : wait_flag_geq<kAcqNone>(p.guard_flag, p.guard_val)) ? 1u : 0u;
-            if (!ok) atomicExch(p.error_flag, 1u);
+            if (!ok) raise_error(p.error_flag);
         }
         ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
     }
@@ -640,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
                     if (p.acquire) asm volatile("fence.proxy.async.global;" ::: "memory");
                     if (!ok) {                                 // timed out: nobody multiplies the stale vector, the host hears of it
                         abort_flag = 1u;
-                        atomicExch(p.error_flag, 1u);
+                        raise_error(p.error_flag);
                     }
                 }
                 // x was written by the kernel in front of this one on the stream (the axpb step of an iterative caller,
@@ -704,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
     if (tl && blockIdx.x == 0 && tid == 0) tl[2] = globaltimer();
     if (p.drain_acc) {
         if (p.wait_y_flag) {                                     // y is still being copied to the host
-            if (lane == 0 && !wait_flag_geq(p.wait_y_flag, p.wait_y_val, false)) atomicExch(p.error_flag, 1u);
+            if (lane == 0 && !wait_flag_geq(p.wait_y_flag, p.wait_y_val, false)) raise_error(p.error_flag);
             __syncwarp();
         }
         const GatherTargets *gt = p.gather;
@@ -729,8 +734,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) spmv_tiles_kernel(const 
 
 template <class A>
 __global__ void drain_kernel(void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end, uint32_t trash_row,
-                             const GatherTargets *gt, uint32_t gather_seq) {
-    drain_rows<A>(acc, y, row_begin, row_end, nullptr, 0u, gt, false, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+                             const GatherTargets *gt, uint32_t gather_seq, uint32_t *y_host, uint32_t y_host_rows) {
+    drain_rows<A>(acc, y, row_begin, row_end, y_host, y_host_rows, gt, false, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     if (blockIdx.x == 0 && threadIdx.x == 0) (void)A::drain(acc, trash_row);
     if (gt) gather_publish(gt, gather_seq);
 }
@@ -738,7 +743,7 @@ __global__ void drain_kernel(void *acc, uint32_t *y, uint32_t row_begin, uint32_
 // root side of the gather: later work on the stream sees the blocks of all ranks
 __global__ void wait_flags_kernel(const uint32_t *flags, uint32_t count, uint32_t val, uint32_t *error_flag) {
     for (uint32_t i = 0; i < count; i++)
-        if (!wait_flag_geq(flags + i, val, true)) atomicExch(error_flag, 1u);
+        if (!wait_flag_geq(flags + i, val, true)) raise_error(error_flag);
 }
 
 // The step between two SpMVs of an iterative caller (PageRank-style x <- alpha (*) A x (+) beta): final y
@@ -867,13 +872,14 @@ cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, uint32_t smem_
 }
 
 cudaError_t launch_drain(int arith, void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end,
-                         uint32_t trash_row, const GatherTargets *gather, uint32_t gather_seq, cudaStream_t stream) {
+                         uint32_t trash_row, const GatherTargets *gather, uint32_t gather_seq, uint32_t *y_host,
+                         uint32_t y_host_rows, cudaStream_t stream) {
     const uint32_t n = row_end > row_begin ? row_end - row_begin : 1;
     const int grid = (int)std::min<uint32_t>((n + 255) / 256, (uint32_t)g_sm_count * 8u);
     if (arith == kArithFixed)
-        drain_kernel<FixedArith><<<grid, 256, 0, stream>>>(acc, y, row_begin, row_end, trash_row, gather, gather_seq);
+        drain_kernel<FixedArith><<<grid, 256, 0, stream>>>(acc, y, row_begin, row_end, trash_row, gather, gather_seq, y_host, y_host_rows);
     else
-        drain_kernel<FloatArith><<<grid, 256, 0, stream>>>(acc, y, row_begin, row_end, trash_row, gather, gather_seq);
+        drain_kernel<FloatArith><<<grid, 256, 0, stream>>>(acc, y, row_begin, row_end, trash_row, gather, gather_seq, y_host, y_host_rows);
     return cudaGetLastError();
 }
 

@@ -125,9 +125,11 @@ struct GatherTargets {
 enum { kArithFixed = 0, kArithFloat = 1 };
 
 cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, uint32_t smem_bytes, cudaStream_t stream);
-// drain only: y[r] = clamp(acc[r]), acc[r] = 0 for r in [row_begin, row_end) and the trash slot
+// drain only: y[r] = clamp(acc[r]), acc[r] = 0 for r in [row_begin, row_end) and the trash slot; y_host (device alias of a
+// mapped page-locked host buffer, or null): rows < y_host_rows are ALSO written there (a download without the copy engine)
 cudaError_t launch_drain(int arith, void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end,
-                         uint32_t trash_row, const GatherTargets *gather, uint32_t gather_seq, cudaStream_t stream);
+                         uint32_t trash_row, const GatherTargets *gather, uint32_t gather_seq, uint32_t *y_host,
+                         uint32_t y_host_rows, cudaStream_t stream);
 // stream-ordered wait (one thread, acquire) until `count` consecutive arrival flags have reached `val`; a
 // timed-out wait raises *error_flag
 cudaError_t launch_wait_flags(const uint32_t *flags, uint32_t count, uint32_t val, uint32_t *error_flag, cudaStream_t stream);
