@@ -105,11 +105,11 @@ __device__ __forceinline__ unsigned long long globaltimer() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// a flag wait timed out: every writer stores the same 1, so a plain system-scope store does (the word lives in mapped
-// page-locked host memory when the flag pipeline is on: the host reads it after a stream synchronisation, no copy)
-__device__ __forceinline__ void raise_error(uint32_t *flag) {
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
-}
+// A flag wait timed out. (An atomic exchange, although every writer stores the same 1 and the word may live in mapped
+// page-locked host memory: a plain `st.relaxed.sys` in its place made the fixed-point kernel 2.6 us slower per SpMV
+// on C2 -- 16.56 against 13.91 us, same box, the store never executed -- one of the code-generation cliffs of a
+// kernel that sits exactly at its 64-register limit.)
+__device__ __forceinline__ void raise_error(uint32_t *flag) { atomicExch(flag, 1u); }
 // kAcqNone: relaxed polls. kAcqSys / kAcqGpu: every poll is an acquire load at that scope, so the successful one
 // synchronises with the writer's release (st.release.sys of a peer GPU's kernel, the copy engine's flag write
 // behind its copy, st.release.gpu of an earlier launch): everything the writer did before raising the flag is
