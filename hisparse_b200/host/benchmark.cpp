@@ -68,8 +68,9 @@ benchmark_result spmv_benchmark(hsb_runtime &runtime, spmv::io::CSRMatrix<float>
     HSB_CHECK(hsb_upload_vector(runtime.ctx, x.data(), mat.num_cols));
     hsb_stats st;
     HSB_CHECK(hsb_get_stats(runtime.ctx, &st));
-    // rotate over enough HBM copies that a timed SpMV never finds its matrix in the 126 MB L2
-    int replicas = (int)std::max<uint64_t>(2, (uint64_t)(2.5 * 126 * 1024 * 1024 / (double)std::max<uint64_t>(st.format_bytes, 1)) + 1);
+    // rotate over enough HBM copies that a timed SpMV never finds its matrix in the L2 (its size is the device's own figure)
+    const double l2_bytes = (double)std::max<size_t>(hsb_device_l2_bytes(g_device), (size_t)32 << 20);
+    int replicas = (int)std::max<uint64_t>(2, (uint64_t)(2.5 * l2_bytes / (double)std::max<uint64_t>(st.format_bytes, 1)) + 1);
     HSB_CHECK(hsb_set_replicas(runtime.ctx, std::min(replicas, 64)));
 
     float step_ms = 0, kernel_ms = 0;

@@ -191,7 +191,7 @@ int hsb_iterate(hsb_ctx *ctx, int iters, uint32_t alpha_word, uint32_t beta_word
 /* ---- measurement and multi-GPU plumbing (no reference counterpart) ------------------------ */
 int hsb_get_stats(hsb_ctx *ctx, hsb_stats *out);
 /* keep n copies of the matrix in HBM and rotate through them on successive hsb_spmv() calls so
- * that a timed loop never re-reads a matrix that is still in the 126 MB L2 */
+ * that a timed loop never re-reads a matrix that is still in the L2 (hsb_device_l2_bytes: 126 MB on B200) */
 int hsb_set_replicas(hsb_ctx *ctx, int n);
 /* CUDA-event timing on the context's stream: `steps` full SpMVs after `warmup` untimed ones.
  * step_ms = (stop - start) / steps over the whole loop; kernel_ms = mean duration of the main

@@ -106,7 +106,7 @@ def main():
             nnz = int(ix.size)
         t_up = time.perf_counter() - t0
         st = ctx.stats()
-        ctx.set_replicas(max(2, int(np.ceil(2.5 * 126 * 2 ** 20 / max(st["format_bytes"], 1)))))
+        ctx.set_replicas(max(2, int(np.ceil(2.5 * (capi.device_l2_bytes(0) or 126 * 2 ** 20) / max(st["format_bytes"], 1)))))
         ctx.upload_vector(np.full(c2, 1 << 24, np.uint32))
         n = max(50, min(2000, int(0.05 / max(1e-6, nnz * 8 / 5e12))))
         ms, _ = ctx.time_spmv(n // 5, n, kernel=False)

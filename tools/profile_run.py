@@ -45,7 +45,7 @@ def main():
     ctx.upload_matrix_csr(r2, c2, ip2, indices, data, on_gpu=a.gpu_format)
     t_up = _t.perf_counter() - t0
     st = ctx.stats()
-    ctx.set_replicas(a.replicas or max(2, int(np.ceil(2.5 * 126 * 2 ** 20 / max(st["format_bytes"], 1)))))
+    ctx.set_replicas(a.replicas or max(2, int(np.ceil(2.5 * (capi.device_l2_bytes(0) or 126 * 2 ** 20) / max(st["format_bytes"], 1)))))
     ctx.upload_vector(x)
     if a.time:
         step, kern = ctx.time_spmv(20, 400)

@@ -25,7 +25,7 @@ else:
     np.savez(cache, r2=r2, c2=c2, ip2=ip2, indices=indices, words=words, xw=xw)
 ctx = capi.Context(0, bench.WORKLOADS[WL][1])
 ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
-ctx.set_replicas(max(2, int(np.ceil(2.5 * 126 * 2 ** 20 / max(ctx.stats()["format_bytes"], 1)))))
+ctx.set_replicas(max(2, int(np.ceil(2.5 * (capi.device_l2_bytes(0) or 126 * 2 ** 20) / max(ctx.stats()["format_bytes"], 1)))))
 ctx.upload_vector(xw)
 n = 2048 if WL in ("c1", "c2", "c3") else 400
 ts = [ctx.time_spmv(n // 8, n, kernel=False)[0] * 1e3 for _ in range(3)]

@@ -42,7 +42,7 @@ def main():
         words, xw = data.view(np.uint32), x.view(np.uint32)
     ctx = capi.Context(0, bench.WORKLOADS[wl][1])
     ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
-    ctx.set_replicas(max(2, int(np.ceil(2.5 * 126 * 2 ** 20 / max(ctx.stats()["format_bytes"], 1)))))
+    ctx.set_replicas(max(2, int(np.ceil(2.5 * (capi.device_l2_bytes(0) or 126 * 2 ** 20) / max(ctx.stats()["format_bytes"], 1)))))
     px = [capi.PinnedArray(c2) for _ in range(2)]
     py = [capi.PinnedArray(r2) for _ in range(2)]
     for b in px:
