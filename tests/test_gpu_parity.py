@@ -889,3 +889,21 @@ def test_timed_out_flag_wait_skips_the_row_updates_and_is_reported(gpu, port):
         a.sync()
     a.close()
     b.close()
+
+
+def test_cpp_benchmark_driver_on_an_npz_dataset(gpu, tmp_path):
+    """The reference's dataset route end to end: a scipy-style `.npz` CSR (compressed, int64
+    index arrays, as datasets/download.sh delivers them) -> the C++ loader (own zlib reader in place of cnpy,
+    sw/data_loader.h:51-70) -> benchmark.cpp's value reset, rounding and VAL_T conversion -> GPU; the driver prints the
+    reference's result line and takes the CPSR route as well (same non-zero count through both)."""
+    import subprocess
+    rows, cols, indptr, indices, data = matgen.rmat_csr(30000, 700000, 61)
+    path = str(tmp_path / "graph_30K_700K_csr_float32.npz")
+    np.savez_compressed(path, shape=np.array([rows, cols], np.int64), data=data, indices=indices.astype(np.int64),
+                        indptr=indptr.astype(np.int64), format=np.array("csr"))
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hisparse_b200", "host")
+    subprocess.run(["make", "-s", "-C", host], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(host, "bin", "benchmark_fixed"), path], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "nnz %d," % indices.size in r.stdout and "same matrix" in r.stdout
+    assert "GOPS }" in r.stdout and "===== Benchmark Finished =====" in r.stdout
