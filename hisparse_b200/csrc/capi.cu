@@ -803,9 +803,15 @@ int hsb_upload_matrix_cpsr(hsb_ctx *c, const void *const ch[HSB_NUM_HBM_CHANNELS
             if (!derr.empty()) return set_err(HSB_EINVAL, "malformed CPSR image: " + derr);
             return set_err(HSB_ECUDA, std::string("GPU decoding failed: ") + cudaGetErrorString(e));
         }
+        const auto t1 = std::chrono::steady_clock::now();
         int rc = upload_device_matrix(c, num_rows, num_cols, nnz, nullptr, d_rows, d_ix, d_v, c->cfg.ob_size);
         cudaFree(d_rows); cudaFree(d_ix); cudaFree(d_v);
         c->preprocess_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        static const bool debug = std::getenv("HSB_DEBUG_PLAN") != nullptr;
+        if (debug)
+            std::fprintf(stderr, "[hsb cpsr] copy + decode of the channel images %.1f ms, format + install %.1f ms\n",
+                         1e3 * std::chrono::duration<double>(t1 - t0).count(),
+                         1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
         return rc;
     }
     std::vector<uint32_t> rows_in(num_row_partitions);
