@@ -851,13 +851,16 @@ def test_cpsr_ingestion_googleplus_size(gpu, port):
     images = m.channel_images(1)
     xw = port.quantize(np.random.default_rng(8).random(c2, dtype=np.float32))
     ctx = capi.Context(0, capi.IMPL_FIXED)
-    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)            # warm-up of the formatter's allocations + the CSR time
-    t0 = time.perf_counter()
-    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
-    t_csr = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    ctx.upload_matrix_cpsr(images, m.n_row_parts, m.n_col_parts, r2, c2)
-    t_cpsr = time.perf_counter() - t0
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)            # warm-up of the formatter's allocations
+    t_csr, t_cpsr = [], []
+    for _ in range(3):                                            # (uploads on a shared host jitter: the best of three counts)
+        t0 = time.perf_counter()
+        ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+        t_csr.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        ctx.upload_matrix_cpsr(images, m.n_row_parts, m.n_col_parts, r2, c2)
+        t_cpsr.append(time.perf_counter() - t0)
+    t_csr, t_cpsr = min(t_csr), min(t_cpsr)
     assert ctx.stats()["nnz"] == indices.size
     ctx.upload_vector(xw)
     ctx.spmv()
