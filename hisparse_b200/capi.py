@@ -57,14 +57,17 @@ def build(force=False):
 
 
 def source_hash():
-    """SHA-256 over the sources that decide what a launch reads from HBM -- the kernels, the format and the
-    planner (csrc/spmv_kernels.*, tile_format.*, gpu_format.cu): identifies a build across recompilations and
-    across changes to the host shim; profiles/traffic.json is keyed by it."""
+    """SHA-256 over the CODE that decides what a launch reads from HBM -- the kernels, the format and the planner
+    (csrc/spmv_kernels.*, tile_format.*, gpu_format.cu), comments and white space stripped: identifies a build across
+    recompilations, comment edits and changes to the host shim; profiles/traffic.json is keyed by it."""
     import hashlib
     h = hashlib.sha256()
     for name in ("spmv_kernels.cu", "spmv_kernels.cuh", "tile_format.cpp", "tile_format.h", "gpu_format.cu"):
+        text = open(os.path.join(HERE, "csrc", name)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
         h.update(name.encode())
-        h.update(open(os.path.join(HERE, "csrc", name), "rb").read())
+        h.update("".join(text.split()).encode())
     return h.hexdigest()
 
 

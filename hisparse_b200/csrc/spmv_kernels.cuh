@@ -94,7 +94,8 @@ struct SpmvParams {
                                   // rotation instead of four: long launches with accumulators too big for L2)
     const uint32_t *guard_flag;   // == done_dev when this launch must see guard_val there before its first row update
     uint32_t guard_val;           // (launch seq - 3 has re-zeroed the accumulator buffer), else null
-    uint32_t *error_flag;         // set to 1 if a flag wait timed out (the launch then proceeds: no hang)
+    uint32_t *error_flag;         // set to 1 if a flag wait timed out (no hang: the launch then makes NO row update; the word
+                                  // is in mapped host memory when the flag pipeline is on, else in device memory)
     unsigned long long *timeline; // optional [256][8] %globaltimer stamps indexed by seq % 256 (profiling aid), or null:
                                   // 0 first CTA start, 1 CTA0 x flag seen, 2 CTA0 predecessor complete, 3 CTA0 drain done,
                                   // 4 CTA0 x tile staged, 5 last CTA end, 6 CTA0 matrix work done
