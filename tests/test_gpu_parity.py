@@ -910,3 +910,68 @@ def test_cpp_benchmark_driver_on_an_npz_dataset(gpu, tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "nnz %d," % indices.size in r.stdout and "same matrix" in r.stdout
     assert "GOPS }" in r.stdout and "===== Benchmark Finished =====" in r.stdout
+
+
+def test_cpsr_upload_rejects_bad_columns_and_recovers(gpu, port):
+    """the on-device decoder refuses a column id beyond the vector buffer / beyond the matrix (HSB_EINVAL, no partial
+    state), and the context takes a well-formed upload afterwards"""
+    cfg = capi.get_config(0)
+    rows, cols, indptr, indices, data = matgen.random_csr(256, 512, 0.05, 9)
+    words = port.quantize(data)
+    m = port.csr2cpsr(rows, cols, indptr, indices, words, 8, cfg.logical_ob_size, cfg.logical_vb_size, 16, False,
+                      hsoracle.VAL_Q824)
+    good = m.channel_images(1)
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    for bad_col in (cfg.logical_vb_size + 5, 600):                 # beyond the vector buffer; inside it but beyond num_cols
+        images = [im.copy() for im in good]
+        im = images[2].reshape(-1, 16)
+        n_hdr = 2                                                  # (1 + IF) header packets per partition, one partition
+        r, k = np.argwhere(im[n_hdr:, :8] != 0xFFFFFFFF)[0]        # a real entry, not a marker
+        im[n_hdr + r, k] = bad_col
+        with pytest.raises(capi.HsbError, match="column"):
+            ctx.upload_matrix_cpsr(images, 1, 1, rows, cols)
+    ctx.upload_matrix_cpsr(good, 1, 1, rows, cols)
+    xw = port.quantize(np.random.default_rng(4).random(cols, dtype=np.float32))
+    ctx.upload_vector(xw)
+    ctx.spmv()
+    assert np.array_equal(ctx.download_result(), port.spmv_q824(indptr, indices, words, xw))
+    ctx.close()
+
+
+def test_two_contexts_interleaved_on_one_device(gpu, port):
+    """two engines (fixed and float) on one GPU, calls interleaved: each keeps its own streams, flags and buffers"""
+    rows, cols, indptr, indices, data = matgen.rmat_csr(8000, 200000, 71)
+    words = port.quantize((data * np.float32(0.1)).astype(np.float32))
+    rng = np.random.default_rng(6)
+    a, b = capi.Context(0, "fixed"), capi.Context(0, "float_pob")
+    a.upload_matrix_csr(rows, cols, indptr, indices, words)
+    b.upload_matrix_csr(rows, cols, indptr, indices, data)
+    for _ in range(3):
+        xf = rng.random(cols, dtype=np.float32)
+        xw = port.quantize(xf)
+        a.upload_vector(xw); b.upload_vector(xf)
+        a.spmv(); b.spmv(); a.spmv(); b.spmv()
+        ya, yb = a.download_result(), b.download_result()
+        assert np.array_equal(ya, port.spmv_q824(indptr, indices, words, xw))
+        check_float(yb, port, indptr, indices, data, xf)
+    a.close(); b.close()
+
+
+def test_float_stall_images_through_the_narrow_layout(gpu, port, monkeypatch):
+    """float_stall channel images (8-way interleave) decoded on the device and formatted into the NARROW layout"""
+    monkeypatch.setenv("HSB_NARROW", "1")
+    cfg = capi.get_config(capi.IMPL_FLOAT_STALL)
+    IF = cfg.interleave_factor
+    rows, cols, indptr, indices, data = matgen.rmat_csr(9000, 150000, 43, values="normal")
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128 * IF, 8)
+    x = np.zeros(c2, np.float32)
+    x[:cols] = np.random.default_rng(2).random(cols, dtype=np.float32) * 2 - 1
+    m = port.csr2cpsr(r2, c2, ip2, indices, data.view(np.uint32), 8, cfg.logical_ob_size, cfg.logical_vb_size,
+                      16 * IF, True, hsoracle.VAL_FLOAT_BITS)
+    ctx = capi.Context(0, capi.IMPL_FLOAT_STALL)
+    ctx.upload_matrix_cpsr(m.channel_images(IF), m.n_row_parts, m.n_col_parts, r2, c2)
+    assert ctx.stats()["layout"] == 1
+    ctx.upload_vector(x)
+    ctx.spmv()
+    check_float(ctx.download_result(), port, ip2, indices, data, x)
+    ctx.close()
