@@ -328,7 +328,7 @@ int install_matrix(hsb_ctx *c, const hsb::TiledMatrix &M, const DeviceMatrix &d,
     // shards: 12.5 M rows) the row updates would all miss; such launches are long anyway, so they rotate two
     // buffers and wait for their predecessor before the first row update instead.
     c->acc_bufs = ((size_t)c->rows + 1) * esz * kAccBuffers > (size_t)96 << 20 ? 2 : kAccBuffers;
-    if (const char *e = std::getenv("HSB_ACC_BUFFERS")) c->acc_bufs = std::atoi(e) == 2 ? 2 : kAccBuffers;
+    if (const char *e = std::getenv("HSB_ACC_BUFFERS")) { const int v = std::atoi(e); c->acc_bufs = v == 1 ? 1 : v == 2 ? 2 : kAccBuffers; }
     for (int b = 0; b < c->acc_bufs; b++) {
         CUDA_TRY(cudaMalloc(&c->d_acc[b], ((size_t)c->rows + 1) * esz));
         CUDA_TRY(cudaMemsetAsync(c->d_acc[b], 0, ((size_t)c->rows + 1) * esz, c->stream));
@@ -443,6 +443,9 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
     // a deferred download rides on a whole-matrix launch only (its successor's drain then rewrites every
     // row of the other y buffer); anything else resolves it the immediate way first
     if (c->pending_dl.active && slot != 0) { int rc = finish(c); if (rc) return rc; }
+    // one accumulator buffer (A/B aid, HSB_ACC_BUFFERS=1): the previous sums are drained by the drain kernel before
+    // this launch may add to the same buffer
+    if (c->acc_bufs == 1 && c->drain_pending) { int rc = finish(c); if (rc) return rc; }
     const DeviceMatrix &m = c->mats[c->next_replica % c->mats.size()];
     c->next_replica++;
     const uint32_t G = (uint32_t)c->sm_count;
@@ -486,7 +489,7 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
     p.seq = ++c->launch_seq;
     p.done_dev = c->d_flags + kFlagDoneDev;
     p.error_flag = c->d_done ? c->d_done + 8 : c->d_flags + kFlagError;
-    if (c->acc_bufs == 2) p.sync_start = 1;
+    if (c->acc_bufs <= 2) p.sync_start = 1;
     else if (p.seq > 3) { p.guard_flag = p.done_dev; p.guard_val = p.seq - 3; }
     p.x = c->d_x[c->x_latest]; p.y = c->d_y[yb];
     if (c->pending_dl.active && c->pending_dl.dev && c->drain_pending) {
