@@ -151,19 +151,24 @@ struct hsb_ctx {
     // flag pipeline (see load_memops): sequence flags in device memory instead of events
     bool flags_mode = false;
     uint32_t *d_flags = nullptr;          // kNumFlags words
-    uint32_t launch_seq = 0;              // SpMV launches so far; launch n publishes n - 1 in done_seq when it starts
-    uint32_t publish_sure = 0;            // highest sequence number that WILL appear in done_seq without further host action
-    uint32_t d2h_wait_seq = 0;            // highest sequence number the download stream has been told to wait for
+    // Launch numbers are 64-bit on the host and travel to the device as their low 32 bits: kernels and stream memory
+    // operations compare flags cyclically ((int32_t)(flag - value) >= 0), which is exact while fewer than 2^31 launches
+    // are in flight, and the host rebuilds the 64-bit number of the last finished launch from the 32-bit word
+    // (done_launch). A context that has issued more than 2^32 launches (C1: five hours) keeps working.
+    uint64_t launch_seq = 0;              // SpMV launches so far; launch n publishes n - 1 in done_seq when it starts
+    uint64_t publish_sure = 0;            // highest sequence number that WILL appear in done_seq without further host action
+    uint64_t d2h_wait_seq = 0;            // highest sequence number the download stream has been told to wait for
+    uint64_t seq_base = 0;                // launch number this context started from (0; HSB_DEBUG_SEQ_BASE: the wrap-around tests)
     bool xwait_once = true;               // stop polling the x flag once a launch that polled it has completed
     bool host_drain = true;               // deferred downloads into page-locked memory are written by the drain itself
-    uint32_t x_reader_seq[kXBuffers] = {0, 0, 0, 0};   // last launch that reads d_x[b]
+    uint64_t x_reader_seq[kXBuffers] = {0, 0, 0, 0};   // last launch that reads d_x[b] (0: none)
     // done_seq lives in mapped page-locked host memory: kernels / stream memory operations write it through
     // d_done, the host polls h_done directly (upload throttling) instead of queueing a stream wait
     volatile uint32_t *h_done = nullptr;
     uint32_t *d_done = nullptr;
     uint32_t x_seq = 0;                   // uploads so far == value written to x_ready[b] when the copy has landed
     int x_wait_buf = -1;                  // buffer whose x_ready flag the next launches wait for (-1: none)
-    uint32_t x_wait_launch = 0;           // first launch that polled the current flag (0: none yet)
+    uint64_t x_wait_launch = 0;           // first launch that polled the current flag (0: none yet)
     uint32_t x_wait_val = 0;
     uint32_t dl_seq = 0, y_dl_seq[2] = {0, 0};   // downloads so far; value y_free[b] reaches when d_y[b] has been read out
     // deferred download; dev != null: `host` is page-locked and mapped, the next launch drains straight into it
@@ -415,9 +420,15 @@ int check_error_flag(hsb_ctx *c) {
 // A launch's completion is normally announced by its successor (after the griddepcontrol.wait at the end of
 // its CTA 0). When there may be no successor (hsb_sync, a second upload in a row, ...) the compute stream
 // announces everything launched so far itself, with a stream memory operation behind the last kernel.
+// 64-bit number of the last launch known to be complete, from the 32-bit word the device publishes: it never
+// exceeds launch_seq and trails it by less than 2^32.
+inline uint64_t done_launch(const hsb_ctx *c) {
+    return c->launch_seq - (uint32_t)((uint32_t)c->launch_seq - *c->h_done);
+}
+
 int publish_done(hsb_ctx *c) {
     if (c->publish_sure == c->launch_seq) return HSB_OK;
-    MEMOP_TRY(g_write32((CUstream)c->stream, (CUdeviceptr)c->d_done, c->launch_seq, 0));
+    MEMOP_TRY(g_write32((CUstream)c->stream, (CUdeviceptr)c->d_done, (uint32_t)c->launch_seq, 0));
     c->publish_sure = c->launch_seq;
     return HSB_OK;
 }
@@ -462,7 +473,7 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
         // download that still reads it
         // every launch that may start before the upload has landed polls its flag; once a launch that
         // polled is known to be complete (the host-visible done_seq) the vector is there for good
-        if (c->x_wait_buf >= 0 && c->xwait_once && c->x_wait_launch && (int32_t)(*c->h_done - c->x_wait_launch) >= 0)
+        if (c->x_wait_buf >= 0 && c->xwait_once && c->x_wait_launch && done_launch(c) >= c->x_wait_launch)
             c->x_wait_buf = -1;
         if (c->x_wait_buf >= 0) {
             p.wait_x_flag = c->d_flags + kFlagXReady + c->x_wait_buf; p.wait_x_val = c->x_wait_val; p.wait_x_count = 1;
@@ -486,11 +497,11 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
             c->y_busy[yb] = false;
         }
     }
-    p.seq = ++c->launch_seq;
+    p.seq = (uint32_t)++c->launch_seq;
     p.done_dev = c->d_flags + kFlagDoneDev;
     p.error_flag = c->d_done ? c->d_done + 8 : c->d_flags + kFlagError;
     if (c->acc_bufs <= 2) p.sync_start = 1;
-    else if (p.seq > 3) { p.guard_flag = p.done_dev; p.guard_val = p.seq - 3; }
+    else if (c->launch_seq - c->seq_base > 3) { p.guard_flag = p.done_dev; p.guard_val = p.seq - 3u; }
     p.x = c->d_x[c->x_latest]; p.y = c->d_y[yb];
     if (c->pending_dl.active && c->pending_dl.dev && c->drain_pending) {
         // page-locked destination: the prologue drain writes the result words to the host buffer as well
@@ -520,7 +531,7 @@ int run_slot(hsb_ctx *c, size_t slot, uint32_t rb, uint32_t re, cudaEvent_t k0, 
         // sequence number appears in done_seq) the download stream copies it out, and from now on the
         // drains go to the other buffer
         MEMOP_TRY(g_wait32((CUstream)c->s_d2h, (CUdeviceptr)c->d_done, p.seq, CU_STREAM_WAIT_VALUE_GEQ));
-        c->d2h_wait_seq = p.seq;
+        c->d2h_wait_seq = c->launch_seq;
         CUDA_TRY(cudaMemcpyAsync(c->pending_dl.host, c->d_y[yb], (size_t)c->pending_dl.n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
         c->y_dl_seq[yb] = ++c->dl_seq;
         MEMOP_TRY(g_write32((CUstream)c->s_d2h, (CUdeviceptr)(c->d_flags + kFlagYFree + yb), c->y_dl_seq[yb], 0));
@@ -650,6 +661,19 @@ hsb_ctx *hsb_create(int device, int impl) {
         if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&c->d_done, hd, 0);
         if (e == cudaSuccess) e = cudaHostAlloc((void **)&c->h_seq_ring, 256 * 4, cudaHostAllocDefault);
         c->flags_mode = e == cudaSuccess;
+        // test aid: start every sequence counter (and the flag words they are compared with) just below a 32-bit
+        // wrap-around instead of at 0, so that a short run crosses it
+        if (const char *v = std::getenv("HSB_DEBUG_SEQ_BASE")) {
+            const uint64_t base = std::strtoull(v, nullptr, 0);
+            const uint32_t b32 = (uint32_t)base;
+            uint32_t init[kNumFlags];
+            for (int i = 0; i < kNumFlags; i++) init[i] = i == kFlagError ? 0u : b32;
+            if (e == cudaSuccess) e = cudaMemcpy(c->d_flags, init, sizeof init, cudaMemcpyHostToDevice);
+            c->h_done[0] = b32;
+            c->seq_base = c->launch_seq = c->publish_sure = c->d2h_wait_seq = base;
+            c->x_seq = c->dl_seq = c->x_wait_val = b32;
+            c->y_dl_seq[0] = c->y_dl_seq[1] = b32;
+        }
         if (const char *v = std::getenv("HSB_XFLAG_COPY")) c->xflag_copy = std::atoi(v);
     }
     if (e != cudaSuccess) {
@@ -844,13 +868,13 @@ int hsb_upload_vector(hsb_ctx *c, const void *x_packed, unsigned num_cols) {
         // done_seq itself -- in steady state the number is already there -- and then queues the copy and
         // the flag that tells the next launch its x has landed.
         const int b = (c->x_latest + 1) % kXBuffers;
-        const uint32_t need = c->x_reader_seq[b];
+        const uint64_t need = c->x_reader_seq[b];
         if (need) {
             if (need > c->publish_sure) { int rc = publish_done(c); if (rc) return rc; }
             const auto t0 = std::chrono::steady_clock::now();
             // bounded back-off: a pause per poll (the mapped word is written over PCIe; hammering it from several
             // ranks' host threads on one socket slows everybody's posted writes), a yield every 64 K polls
-            for (unsigned spins = 0; (int32_t)(*c->h_done - need) < 0; spins++) {
+            for (unsigned spins = 0; done_launch(c) < need; spins++) {
 #if defined(__x86_64__) || defined(__i386__)
                 __builtin_ia32_pause();
 #endif

@@ -975,3 +975,41 @@ def test_float_stall_images_through_the_narrow_layout(gpu, port, monkeypatch):
     ctx.spmv()
     check_float(ctx.download_result(), port, ip2, indices, data, x)
     ctx.close()
+
+
+@pytest.mark.parametrize("base", [(1 << 32) - 40, (1 << 31) - 40, (3 << 32) - 7], ids=["2^32", "2^31", "3*2^32"])
+def test_sequence_numbers_cross_a_32_bit_wrap(gpu, port, monkeypatch, base):
+    """A context whose launch / upload / download numbers start just below a 32-bit wrap-around (HSB_DEBUG_SEQ_BASE):
+    the flag words on the device are 32-bit and compared cyclically, the host keeps 64-bit numbers. The pipelined
+    sequence, repeated launches on one vector and the iteration must all run across the wrap with exact results."""
+    monkeypatch.setenv("HSB_DEBUG_SEQ_BASE", str(base))
+    rows, cols, indptr, indices, data = matgen.rmat_csr(3000, 40000, 37)
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
+    words = port.quantize(data)
+    rng = np.random.default_rng(12)
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    monkeypatch.delenv("HSB_DEBUG_SEQ_BASE")
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+    n = 24
+    xs = [capi.PinnedArray(c2) for _ in range(n)]
+    ys = [capi.PinnedArray(r2) for _ in range(n)]
+    for k in range(n):
+        xs[k].array[:] = port.quantize(rng.random(c2, dtype=np.float32))
+    wants = [port.spmv_q824(ip2, indices, words, b.array) for b in xs]
+    for k in range(n):                                   # 24 uploads, launches and downloads: up to base + 24
+        ctx.upload_vector(xs[k].array)
+        ctx.spmv()
+        ctx.download_result_async(ys[k].array)
+    ctx.sync()
+    for k in range(n):
+        assert np.array_equal(ys[k].array, wants[k]), k
+    for k in (5, 6):                                     # 2 x 37 launches on one vector: crosses the wrap
+        ctx.upload_vector(xs[k].array)
+        for _ in range(37):
+            ctx.spmv()
+        assert np.array_equal(ctx.download_result(), wants[k]), k
+    ctx.time_e2e([xs[0].array, xs[1].array], [ys[0].array, ys[1].array], 200, async_download=True)
+    assert np.array_equal(ys[0].array, wants[0]) and np.array_equal(ys[1].array, wants[1])
+    ctx.time_e2e([xs[2].array, xs[3].array], [ys[2].array, ys[3].array], 50, async_download=False)
+    assert np.array_equal(ys[2].array, wants[2]) and np.array_equal(ys[3].array, wants[3])
+    ctx.close()
