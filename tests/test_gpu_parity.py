@@ -1013,3 +1013,84 @@ def test_sequence_numbers_cross_a_32_bit_wrap(gpu, port, monkeypatch, base):
     ctx.time_e2e([xs[2].array, xs[3].array], [ys[2].array, ys[3].array], 50, async_download=False)
     assert np.array_equal(ys[2].array, wants[2]) and np.array_equal(ys[3].array, wants[3])
     ctx.close()
+
+
+def test_contexts_release_their_device_memory(gpu, port):
+    """create / upload / run / destroy twenty times (CSR, CPSR images, re-upload into a live context): free device
+    memory ends where it started (within the allocator's granularity), i.e. no per-context or per-matrix leak"""
+    import torch
+    rows, cols, indptr, indices, data = matgen.rmat_csr(20000, 600000, 41)
+    r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
+    words = port.quantize(data)
+    x = port.quantize(np.random.default_rng(4).random(c2, dtype=np.float32))
+    want = port.spmv_q824(ip2, indices, words, x)
+    cfg = capi.get_config(capi.IMPL_FIXED)
+    m = port.csr2cpsr(r2, c2, ip2, indices, words, 8, cfg.logical_ob_size, cfg.logical_vb_size, 16, True, hsoracle.VAL_Q824)
+
+    def once(k):
+        ctx = capi.Context(0, capi.IMPL_FIXED)
+        if k % 3 == 2:
+            ctx.upload_matrix_cpsr(m.channel_images(1), m.n_row_parts, m.n_col_parts, r2, c2)
+        else:
+            ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+        if k % 3 == 1:
+            ctx.upload_matrix_csr(r2, c2, ip2, indices, words)       # replaces the matrix of a live context
+        ctx.set_replicas(2)
+        ctx.upload_vector(x)
+        ctx.spmv(); ctx.spmv()
+        assert np.array_equal(ctx.download_result(), want), k
+        ctx.close()
+
+    once(0); once(1); once(2)                       # warm the allocator and the kernel images
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    for k in range(20):
+        once(k)
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info(0)[0]
+    assert free0 - free1 < (8 << 20), (free0, free1)
+
+
+def test_two_host_threads_two_contexts(gpu, port):
+    """two host threads, each driving its own context through the pipelined upload / SpMV / download sequence at the
+    same time (ctypes drops the GIL inside the calls): per-context state only, the last-error string is per thread"""
+    import threading
+    mats = []
+    for seed, rows_, nnz_ in ((51, 6000, 90000), (52, 15000, 400000)):
+        rows, cols, indptr, indices, data = matgen.rmat_csr(rows_, nnz_, seed)
+        r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 8)
+        words = port.quantize(data)
+        rng = np.random.default_rng(seed)
+        xs = [port.quantize(rng.random(c2, dtype=np.float32)) for _ in range(2)]
+        mats.append((r2, c2, ip2, indices, words, xs, [port.spmv_q824(ip2, indices, words, x) for x in xs]))
+    errors = []
+
+    def drive(t):
+        try:
+            r2, c2, ip2, indices, words, xs, wants = mats[t]
+            ctx = capi.Context(0, capi.IMPL_FIXED)
+            ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+            px = [capi.PinnedArray(c2) for _ in range(2)]
+            py = [capi.PinnedArray(r2) for _ in range(2)]
+            for k in range(2):
+                px[k].array[:] = xs[k]
+            for rep in range(6):
+                ctx.time_e2e([b.array for b in px], [b.array for b in py], 400, async_download=rep % 2 == 0)
+                for k in range(2):
+                    if not np.array_equal(py[k].array, wants[k]):
+                        errors.append((t, rep, k))
+                for k in range(2):
+                    ctx.upload_vector(px[k].array); ctx.spmv()
+                    if not np.array_equal(ctx.download_result(), wants[k]):
+                        errors.append((t, rep, k, "sync"))
+            # an error in this thread must not show up in the other one's hsb_last_error
+            with pytest.raises(capi.HsbError):
+                ctx.upload_vector(np.zeros(3, np.uint32))
+            ctx.close()
+        except Exception as e:                      # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    th = [threading.Thread(target=drive, args=(t,)) for t in range(2)]
+    for t in th: t.start()
+    for t in th: t.join()
+    assert not errors, errors
