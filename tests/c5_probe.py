@@ -2,7 +2,7 @@
 generated on the device, formatted on the device, multiplied, and checked against the oracle on the
 host (full size: the oracle's C loop does 250 M MACs in about a second).
 
-    python tools/c5_probe.py [--rows 12500000] [--cols 100000000] [--impl fixed|float_pob] [--no-check]
+    python tests/c5_probe.py [--rows 12500000] [--cols 100000000] [--impl fixed|float_pob] [--no-check]
 
 Prints one JSON line per run. Not a bench line (bench.py is); used to fill DESIGN.md's C5 table."""
 import argparse

@@ -1,8 +1,8 @@
 """PageRank-style power iteration x <- alpha (*) A x (+) beta on 1..N GPUs (the
 caller either side of the SpMV in the reference's intended use, unit_tests/test_app.cpp:51-136).
 
-    python tools/pagerank.py [--nodes 576289 --nnz 42460000 --iters 20 --impl float_pob]
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/pagerank.py ...
+    python tests/pagerank.py [--nodes 576289 --nnz 42460000 --iters 20 --impl float_pob]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/pagerank.py ...
 
 One process per GPU. The link matrix (R-MAT, value 1/out-degree) is cut into nnz-balanced row blocks;
 every rank keeps its block resident plus a replica of x. Per iteration: hsb_spmv on the block,

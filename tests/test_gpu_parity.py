@@ -561,7 +561,7 @@ def test_iterate_float(gpu, port):
 def test_iterate_two_row_block_shards(gpu, port):
     """The multi-GPU iteration on one device: two contexts hold the two row-block shards, each writes its
     slice of the next vector at its row offset (hsb_axpb_to_vector), the slices are exchanged (the
-    all-gather of tools/pagerank.py) and committed. Bit-equal to the single-context iteration."""
+    all-gather of tests/pagerank.py) and committed. Bit-equal to the single-context iteration."""
     import torch
     from hisparse_b200 import sharding
     r2, c2, ip2, indices, data = _pagerank_matrix(5000, 70000, 45)
@@ -606,7 +606,7 @@ def test_iterate_two_row_block_shards(gpu, port):
 
 def test_peer_iteration_single_rank(gpu, port):
     """hsb_peer_export / hsb_peer_connect / hsb_axpb_to_peers with a world of one (the multi-GPU runs are
-    tools/pagerank.py --p2p --check under torchrun): same kernel, same arrival-flag wait, bit-exact."""
+    tests/pagerank.py --p2p --check under torchrun): same kernel, same arrival-flag wait, bit-exact."""
     from hisparse_b200 import sharding
     r2, c2, ip2, indices, data = _pagerank_matrix(6000, 90000, 47)
     words = port.quantize(data)

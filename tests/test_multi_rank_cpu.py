@@ -77,7 +77,7 @@ def test_shard_bounds_balance():
 def _pagerank_worker(rank, world, port_no, out_dir):
     """x <- alpha (*) A x (+) beta over row-block shards: every rank multiplies its shard, writes its slice
     of the next vector at its row offset and the slices are all-gathered in place -- the loop of
-    tools/pagerank.py with the oracle standing in for the GPU engine."""
+    tests/pagerank.py with the oracle standing in for the GPU engine."""
     sys.path.insert(0, ROOT)
     from hisparse_b200 import matgen, sharding
     from oracle import hsoracle

@@ -15,7 +15,7 @@ ncu -i gpurun_out/${T}_c2_full.ncu-rep --page raw --csv > gpurun_out/${T}_c2_ful
 ncu --replay-mode app-range --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,dram__bytes.sum.per_second \
     --clock-control none --csv --page raw --log-file gpurun_out/${T}_range_c2.csv python tools/profile_run.py --range 512 > /dev/null 2>&1
 ncu --set full --import-source on --clock-control none -k regex:spmv_tiles --launch-skip 4 -c 1 -o gpurun_out/${T}_c5_full \
-    python tools/c5_probe.py --impl float_pob --no-check --steps 3 > /dev/null 2>&1
+    python tests/c5_probe.py --impl float_pob --no-check --steps 3 > /dev/null 2>&1
 ncu -i gpurun_out/${T}_c5_full.ncu-rep --page details > gpurun_out/${T}_ncu_full_c5shard_narrow.txt 2>/dev/null
 python tools/ncu_traffic.py --kernel-csv gpurun_out/${T}_c2_full_raw.csv --range-csv gpurun_out/${T}_range_c2.csv --range-spmvs 512 \
     --out gpurun_out/${T}_traffic.json

@@ -16,5 +16,5 @@ except Exception as e:
     print("$f", "FAILED", e, open("gpurun_out/$f.json").read()[:300])
 PY
 done
-timeout 300 $T tools/pagerank.py --iters 20 2>&1 | tail -1
-timeout 300 $T tools/pagerank.py --iters 20 --impl fixed --nodes 107614 --nnz 13670000 2>&1 | tail -1
+timeout 300 $T tests/pagerank.py --iters 20 2>&1 | tail -1
+timeout 300 $T tests/pagerank.py --iters 20 --impl fixed --nodes 107614 --nnz 13670000 2>&1 | tail -1

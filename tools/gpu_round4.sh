@@ -15,5 +15,5 @@ except Exception as e:
     print("$f", "FAILED", e, open("gpurun_out/$f.json").read()[:300]); print(open("gpurun_out/" + ("b$N.err" if "$f" == "bench_n$N" else "b${N}c4.err")).read()[-800:])
 PY
 done
-timeout 300 $T tools/pagerank.py --iters 50 --p2p 2>&1 | tail -1
-timeout 300 $T tools/pagerank.py --iters 50 --impl fixed --nodes 107614 --nnz 13670000 --check --p2p 2>&1 | tail -1
+timeout 300 $T tests/pagerank.py --iters 50 --p2p 2>&1 | tail -1
+timeout 300 $T tests/pagerank.py --iters 50 --impl fixed --nodes 107614 --nnz 13670000 --check --p2p 2>&1 | tail -1
