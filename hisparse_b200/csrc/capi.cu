@@ -82,7 +82,7 @@ bool load_memops() {
             return set_err(HSB_ECUDA, b__);                                                         \
         }                                                                                           \
     } while (0)
-enum { kFlagXReady = 0, kFlagYFree = 4, kFlagError = 6, kFlagDoneDev = 7, kNumFlags = 8, kXBuffers = 4, kAccBuffers = 4 };
+enum { kFlagXReady = 0, kFlagYFree = 4, kFlagError = 6, kFlagDoneDev = 7, kFlagIterBarrier = 8, kNumFlags = 16, kXBuffers = 4, kAccBuffers = 4 };
 
 struct DeviceMatrix {
     uint32_t *vals = nullptr;
@@ -186,6 +186,7 @@ struct hsb_ctx {
     // "x has landed" flag written by a 4-byte copy from a ring of page-locked sequence words instead of a stream
     // memory operation (hsb_set_option "xflag_copy"): a pure copy-engine operation behind the vector's copy
     int xflag_copy = 1;
+    bool iterate_persistent = true;       // hsb_iterate as one cooperative launch (hsb_set_option "iterate_persistent", HSB_ITERATE_PERSISTENT)
     uint32_t *h_seq_ring = nullptr;       // 256 page-locked words; slot (seq & 255) holds seq while its copy may be in flight
     // rows + 1 accumulators (uint64 fixed / fp32 float) x 4 in rotation: launch n adds into buffer n % 4 and,
     // at its very end, drains buffer (n - 1) % 4 (its predecessor's sums) into y and re-zeroes it. Four, because
@@ -646,6 +647,7 @@ hsb_ctx *hsb_create(int device, int impl) {
     e = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_h2d_b, cudaStreamNonBlocking);
     for (int i = 0; i < 2; i++) if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_h2d_more[i], cudaStreamNonBlocking);
+    if (const char *v = std::getenv("HSB_ITERATE_PERSISTENT")) c->iterate_persistent = std::atoi(v) != 0;
     if (const char *v = std::getenv("HSB_UPLOAD_STREAMS")) c->n_upload_streams = std::min(4, std::max(1, std::atoi(v)));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
     cudaEvent_t *evs[] = {&c->ev_xready, &c->ev_xfree[0], &c->ev_xfree[1], &c->ev_yready, &c->ev_ydone};
@@ -667,7 +669,7 @@ hsb_ctx *hsb_create(int device, int impl) {
             const uint64_t base = std::strtoull(v, nullptr, 0);
             const uint32_t b32 = (uint32_t)base;
             uint32_t init[kNumFlags];
-            for (int i = 0; i < kNumFlags; i++) init[i] = i == kFlagError ? 0u : b32;
+            for (int i = 0; i < kNumFlags; i++) init[i] = (i == kFlagError || i >= kFlagIterBarrier) ? 0u : b32;
             if (e == cudaSuccess) e = cudaMemcpy(c->d_flags, init, sizeof init, cudaMemcpyHostToDevice);
             c->h_done[0] = b32;
             c->seq_base = c->launch_seq = c->publish_sure = c->d2h_wait_seq = base;
@@ -1390,10 +1392,76 @@ int hsb_axpb_to_peers(hsb_ctx *c, uint32_t alpha_word, uint32_t beta_word, uint3
     return HSB_OK;
 }
 
+namespace {
+// hsb_iterate as ONE cooperative launch (spmv_iterate_kernel): the grid stays resident and the two dependencies of an
+// iteration are grid-wide barriers instead of kernel boundaries. HSB_ITERATE_PERSISTENT=0: the launch-per-step form.
+int iterate_persistent(hsb_ctx *c, int iters, uint32_t alpha_word, uint32_t beta_word) {
+    CUDA_TRY(cudaSetDevice(c->device));
+    { int rc = finish(c); if (rc) return rc; }             // y final, every accumulator buffer zero, deferred download issued
+    // the vector the first iteration reads has landed, and no upload is writing the buffer the iterations alternate with
+    CUDA_TRY(cudaStreamSynchronize(c->s_h2d));
+    CUDA_TRY(cudaStreamSynchronize(c->s_h2d_b));
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamSynchronize(c->s_h2d_more[i]));
+    c->x_wait_buf = -1; c->x_dirty = false;
+    const int yb = c->y_cur;
+    if (c->y_busy[yb]) {                                   // a download still reads y: order the rewrite behind it
+        if (c->flags_mode)
+            MEMOP_TRY(g_wait32((CUstream)c->stream, (CUdeviceptr)(c->d_flags + kFlagYFree + yb), c->y_dl_seq[yb], CU_STREAM_WAIT_VALUE_GEQ));
+        else
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_ydone, 0));
+        c->y_busy[yb] = false;
+    }
+    const int nb = c->flags_mode ? kXBuffers : 2;
+    const DeviceMatrix &m = c->mats[c->next_replica % c->mats.size()];
+    c->next_replica++;
+    const uint32_t G = (uint32_t)c->sm_count;
+    const int grid = (int)c->plan_grid[0];
+    while (iters > 0) {
+        const int n = std::min(iters, 1 << 20);            // the barrier counter: 2 * grid per iteration, below 2^31
+        const int b = (c->x_latest + 1) % nb;
+        hsb::SpmvParams p;
+        std::memset(&p, 0, sizeof p);
+        p.vals = m.vals; p.cols = m.cols; p.slice_rows = m.slice_rows;
+        p.cta_seg = c->d_cta_seg;
+        p.segs = c->d_segs;
+        p.seq = (uint32_t)++c->launch_seq;
+        p.done_dev = c->d_flags + kFlagDoneDev;
+        p.done_seq = c->flags_mode ? c->d_done : nullptr;
+        p.error_flag = c->d_done ? c->d_done + 8 : c->d_flags + kFlagError;
+        p.y = c->d_y[yb];
+        p.acc = c->d_acc[c->acc_cur];
+        p.narrow = c->meta.narrow ? 1u : 0u;
+        p.comb_offset = c->comb_offset;
+        p.trash_row = c->rows;
+        hsb::IterateParams it;
+        it.x0 = c->d_x[c->x_latest]; it.x1 = c->d_x[b];
+        it.barrier = c->d_flags + kFlagIterBarrier;
+        it.iters = (uint32_t)n; it.alpha = alpha_word; it.beta = beta_word;
+        it.rows = c->rows; it.x_limit = c->x_words;
+        CUDA_TRY(cudaMemsetAsync(it.barrier, 0, 4, c->stream));
+        CUDA_TRY(hsb::launch_iterate(c->arith, p, it, grid, c->smem_bytes, c->stream));
+        c->launches++;
+        // both buffers were read by this launch; its number appears in done_seq through the stream operation below
+        c->x_reader_seq[c->x_latest] = c->x_reader_seq[b] = c->launch_seq;
+        if (n & 1) c->x_latest = b;
+        iters -= n;
+    }
+    (void)G;
+    if (c->flags_mode) { int rc = publish_done(c); if (rc) return rc; }
+    else CUDA_TRY(cudaEventRecord(c->ev_xfree[c->x_latest ^ 1], c->stream));
+    // the next SpMV is a programmatic launch that stages x before its griddepcontrol.wait: it has to wait for this grid first
+    c->x_after_grid = true;
+    c->x_next_buf = -1;
+    return HSB_OK;
+}
+}  // namespace
+
 int hsb_iterate(hsb_ctx *c, int iters, uint32_t alpha_word, uint32_t beta_word) {
     if (!c || iters < 0) return set_err(HSB_EINVAL, "bad argument");
     if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
     if (c->rows > c->x_words) return set_err(HSB_EINVAL, "hsb_iterate needs rows <= columns (x <- f(A x))");
+    // (a gather of y rides on the drains of the launch-per-step form; a pending update of the next vector belongs to it too)
+    if (c->iterate_persistent && iters > 0 && !c->d_gather && c->x_next_buf < 0) return iterate_persistent(c, iters, alpha_word, beta_word);
     for (int k = 0; k < iters; k++) {
         int rc = hsb_spmv(c);
         if (rc == HSB_OK) rc = hsb_axpb_to_vector(c, alpha_word, beta_word, 0);
@@ -1418,6 +1486,8 @@ int hsb_set_option(hsb_ctx *c, const char *name, int value) {
         c->x_wait_buf = -1; c->x_dirty = false;
         for (int b = 0; b < kXBuffers; b++) c->x_reader_seq[b] = 0;
         for (int b = 0; b < 2; b++) CUDA_TRY(cudaEventRecord(c->ev_xfree[b], c->stream));
+    } else if (n == "iterate_persistent") {
+        c->iterate_persistent = value != 0;
     } else if (n == "xwait_once") {
         c->xwait_once = value != 0;
     } else if (n == "host_drain") {

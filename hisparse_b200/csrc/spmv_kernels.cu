@@ -799,6 +799,9 @@ int g_sm_count = 148;                 // configure_kernels() replaces it with th
 
 }  // namespace
 
+// hsb_iterate as one cooperative launch: kernel + launcher, built from the device functions above
+#include "spmv_iterate.cuh"
+
 cudaError_t launch_wait_flags(const uint32_t *flags, uint32_t count, uint32_t val, uint32_t *error_flag, cudaStream_t stream) {
     wait_flags_kernel<<<1, 1, 0, stream>>>(flags, count, val, error_flag);
     return cudaGetLastError();
@@ -848,7 +851,7 @@ cudaError_t configure_kernels(int sm_count) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) return e;
     }
-    return cudaSuccess;
+    return configure_iterate_kernels();
 }
 
 cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, uint32_t smem_bytes, cudaStream_t stream) {

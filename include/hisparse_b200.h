@@ -185,7 +185,11 @@ int hsb_download_gathered(hsb_ctx *ctx, void *y_packed, uint32_t total_rows);
 int hsb_device_numa_node(int device);
 /* L2 cache size of the device in bytes (0 on error): what a timed loop's working set has to exceed */
 size_t hsb_device_l2_bytes(int device);
-/* single GPU, rows <= cols: iters x { hsb_spmv; hsb_axpb_to_vector(alpha, beta, 0); hsb_vector_commit } */
+/* single GPU, rows <= cols: iters x { hsb_spmv; hsb_axpb_to_vector(alpha, beta, 0); hsb_vector_commit } -- the same
+ * results, issued as ONE cooperative launch whose grid stays resident: the two dependencies of an iteration (all row
+ * updates before the drain, the whole new vector before the next SpMV) are grid-wide barriers instead of kernel
+ * boundaries. Afterwards y = A x of the last iteration (hsb_download_result) and the current vector is the updated one.
+ * hsb_set_option "iterate_persistent" 0 (or a gather of y being connected) selects the launch-per-step form. */
 int hsb_iterate(hsb_ctx *ctx, int iters, uint32_t alpha_word, uint32_t beta_word);
 
 /* ---- measurement and multi-GPU plumbing (no reference counterpart) ------------------------ */
@@ -209,7 +213,7 @@ int hsb_time_e2e(hsb_ctx *ctx, const void *const x_host[2], void *const y_host[2
  * page-locked memory are written by the kernel's drain itself instead of the copy engine (default); "acquire":
  * 1 = the kernels' flag waits are acquire loads + fence.proxy.async (default), 0 = relaxed (A/B aid); "xflag_copy":
  * 1 = the "vector has landed" flag is written by a 4-byte copy behind the vector's copy (default), 0 = by a stream
- * memory operation. */
+ * memory operation; "iterate_persistent": 1 = hsb_iterate is one cooperative launch (default), 0 = a launch per step. */
 int hsb_set_option(hsb_ctx *ctx, const char *name, int value);
 /* Profiling aid: SM-clock stamps of the last launch, [sm_count][34] = per warp "my slices are done",
  * then CTA "finished" (wait for the predecessor and drain included); the last word is unused. out == NULL arms (capacity != 0) or

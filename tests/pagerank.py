@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--nnz", type=int, default=42_460_000)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--impl", default="float_pob", choices=["fixed", "float_pob", "float_stall"])
+    ap.add_argument("--step-form", action="store_true", help="one GPU: hsb_iterate as a launch per step instead of one cooperative launch")
     ap.add_argument("--check", action="store_true", help="compare with a host iteration (oracle; small sizes)")
     ap.add_argument("--p2p", action="store_true",
                     help="N > 1: exchange the x blocks inside the update kernel over peer memory (hsb_axpb_to_peers) "
@@ -64,6 +65,8 @@ def main():
     ctx.upload_matrix_csr(bounds[rank + 1] - bounds[rank], c2, sip, six, sw)
     ctx.upload_vector(x0)
     ctx.sync()
+    if args.step_form:
+        ctx.set_option("iterate_persistent", 0)
     p2p = args.p2p and dist is not None
     if p2p:
         mine = torch.from_numpy(ctx.peer_export()).cuda(local)
@@ -79,6 +82,11 @@ def main():
                 ctx.spmv()
                 ctx.axpb_to_peers(alpha, beta, bounds[rank])
                 ctx.vector_commit()
+            ctx.sync()
+            return
+        if dist is None:
+            # one GPU: hsb_iterate -- one cooperative launch for all n iterations (--step-form: a launch per step)
+            ctx.iterate(n, alpha, beta)
             ctx.sync()
             return
         for _ in range(n):
@@ -105,7 +113,7 @@ def main():
     out = {"nodes": r2, "nnz": int(ip2[-1]), "impl": args.impl, "n_gpus": world, "iters": args.iters,
            "ms_per_iteration": 1e3 * sec, "gops": 2.0 * int(ip2[-1]) / sec / 1e9,
            "exchange": "peer-memory stores + arrival flags inside the update kernel" if p2p else
-                       ("NCCL broadcasts issued by the host" if world > 1 else "none (single GPU)"),
+                       ("NCCL broadcasts issued by the host" if world > 1 else ("none (single GPU, launch per step)" if args.step_form else "none (single GPU, one cooperative launch)")),
            "what": "spmv + fused drain/axpb + exchange of the x blocks + commit, per iteration"}
     if args.check:
         from oracle import hsoracle

@@ -1094,3 +1094,119 @@ def test_two_host_threads_two_contexts(gpu, port):
     for t in th: t.start()
     for t in th: t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("narrow", [0, 1], ids=["wide", "narrow"])
+@pytest.mark.parametrize("n,nnz", [(600, 9000), (6000, 90000), (60000, 1500000)])
+def test_iterate_one_launch_against_oracle_and_step_form(gpu, port, monkeypatch, narrow, n, nnz):
+    """hsb_iterate as ONE cooperative launch (grid barriers between the SpMV and the update of x): the vector after k
+    iterations, y of the last iteration and the following SpMV are bit-equal to the oracle's iteration and to the
+    launch-per-step form; odd and even iteration counts (the two x buffers swap), calls mixed with uploads, downloads
+    and plain SpMVs, both layouts."""
+    monkeypatch.setenv("HSB_NARROW", str(narrow))
+    r2, c2, ip2, indices, data = _pagerank_matrix(n, nnz, 61 + narrow)
+    words = port.quantize(data)
+    alpha, beta = int(port.quantize(np.float32([0.85]))[0]), int(port.quantize(np.float32([0.15 / 8]))[0])
+    x0 = port.quantize(np.full(c2, 1.0 / 8, np.float32))
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+    assert ctx.stats()["layout"] == narrow
+    ref = capi.Context(0, capi.IMPL_FIXED)
+    ref.upload_matrix_csr(r2, c2, ip2, indices, words)
+    ref.set_option("iterate_persistent", 0)
+    x = x0.copy()
+    done = 0
+    ctx.upload_vector(x0); ref.upload_vector(x0)
+    for k in (1, 2, 5, 4):
+        ctx.iterate(k, alpha, beta); ref.iterate(k, alpha, beta)
+        for _ in range(k):
+            y = port.spmv_q824(ip2, indices, words, x)
+            x = hsoracle.axpb_q824(alpha, y, beta)
+        done += k
+        got_y = ctx.download_result()
+        assert np.array_equal(got_y, y), (done, "y of the last iteration")
+        assert np.array_equal(ref.download_result(), y), (done, "step form")
+        ctx.spmv(); ref.spmv()
+        want = port.spmv_q824(ip2, indices, words, x)
+        assert np.array_equal(ctx.download_result(), want), (done, "SpMV on the iterated vector")
+        assert np.array_equal(ref.download_result(), want), (done, "step form")
+    # a fresh upload restarts the iteration; a pinned, deferred download sits between the calls
+    py = capi.PinnedArray(r2)
+    ctx.upload_vector(x0)
+    ctx.spmv()
+    ctx.download_result_async(py.array)
+    ctx.iterate(3, alpha, beta)
+    ctx.sync()
+    assert np.array_equal(py.array, port.spmv_q824(ip2, indices, words, x0))
+    x = x0.copy()
+    for _ in range(3):
+        y = port.spmv_q824(ip2, indices, words, x)
+        x = hsoracle.axpb_q824(alpha, y, beta)
+    assert np.array_equal(ctx.download_result(), y)
+    ctx.spmv()                                            # the step form continues from the state the launch left
+    ctx.axpb_to_vector(alpha, beta, 0)
+    ctx.vector_commit()
+    ctx.spmv()
+    x = hsoracle.axpb_q824(alpha, port.spmv_q824(ip2, indices, words, x), beta)
+    assert np.array_equal(ctx.download_result(), port.spmv_q824(ip2, indices, words, x))
+    ctx.close(); ref.close()
+
+
+def test_iterate_one_launch_float_equals_step_form(gpu, port):
+    """fp32: the cooperative launch and the launch-per-step form run the same arithmetic; row updates are atomic adds in
+    no fixed order, so the two agree within the tolerance of the path (compounded over the iterations), not bit for bit"""
+    r2, c2, ip2, indices, data = _pagerank_matrix(20000, 500000, 67)
+    alpha, beta = np.float32(0.85), np.float32(0.15 / r2)
+    x0 = np.full(c2, 1.0 / r2, np.float32)
+    outs = []
+    for persistent in (1, 0):
+        ctx = capi.Context(0, capi.IMPL_FLOAT_POB)
+        ctx.upload_matrix_csr(r2, c2, ip2, indices, data)
+        ctx.set_option("iterate_persistent", persistent)
+        ctx.upload_vector(x0)
+        ctx.iterate(9, int(alpha.view(np.uint32)), int(beta.view(np.uint32)))
+        outs.append(ctx.download_result().view(np.float32).astype(np.float64))
+        ctx.close()
+    x = x0.astype(np.float64)
+    for _ in range(9):
+        y64, sa = port.spmv_f64(ip2, indices, data, x.astype(np.float32))
+        x = float(alpha) * y64 + float(beta)
+    for y in outs:
+        assert np.all(np.abs(y - y64) <= 1e-4 * sa + 1e-12)
+
+
+def test_two_contexts_iterate_concurrently(gpu, port):
+    """two host threads, two contexts, both inside hsb_iterate at the same time: each cooperative launch needs every SM
+    for its grid barriers, so the two grids must never be resident half and half (the launches are gang-scheduled);
+    both finish with exact results, no barrier time-out"""
+    import threading
+    r2, c2, ip2, indices, data = _pagerank_matrix(40000, 1200000, 71)
+    words = port.quantize(data)
+    alpha, beta = int(port.quantize(np.float32([0.85]))[0]), int(port.quantize(np.float32([0.15 / 8]))[0])
+    x0 = port.quantize(np.full(c2, 1.0 / 8, np.float32))
+    iters = 60
+    x = x0.copy()
+    for _ in range(iters):
+        y = port.spmv_q824(ip2, indices, words, x)
+        x = hsoracle.axpb_q824(alpha, y, beta)
+    ctxs = [capi.Context(0, capi.IMPL_FIXED) for _ in range(2)]
+    for c in ctxs:
+        c.upload_matrix_csr(r2, c2, ip2, indices, words)
+        c.upload_vector(x0)
+        c.sync()
+    errors = []
+
+    def drive(c):
+        try:
+            for _ in range(6):
+                c.iterate(iters // 6, alpha, beta)
+            if not np.array_equal(c.download_result(), y):
+                errors.append("mismatch")
+        except Exception as e:                      # noqa: BLE001
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=drive, args=(c,)) for c in ctxs]
+    for t in th: t.start()
+    for t in th: t.join()
+    for c in ctxs: c.close()
+    assert not errors, errors
