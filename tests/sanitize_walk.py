@@ -53,6 +53,12 @@ for _ in range(3):
     x = hsoracle.axpb_q824(alpha, port.spmv_q824(sip2, sq[3], sw, x), beta)
 ctx.spmv()
 assert np.array_equal(ctx.download_result(), port.spmv_q824(sip2, sq[3], sw, x))
+ctx.set_option("iterate_persistent", 0)                           # the launch-per-step form continues the iteration
+ctx.iterate(2, alpha, beta)
+for _ in range(2):
+    x = hsoracle.axpb_q824(alpha, port.spmv_q824(sip2, sq[3], sw, x), beta)
+ctx.spmv()
+assert np.array_equal(ctx.download_result(), port.spmv_q824(sip2, sq[3], sw, x))
 ctx.close()
 
 # float
