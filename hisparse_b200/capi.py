@@ -126,6 +126,7 @@ def lib():
     L.hsb_device_x_next.restype = vp
     L.hsb_vector_commit.argtypes = [vp]
     L.hsb_iterate.argtypes = [vp, C.c_int, u32, u32]
+    L.hsb_iterate_peers.argtypes = [vp, C.c_int, u32, u32, u32]
     L.hsb_peer_export.argtypes = [vp, vp]
     L.hsb_peer_connect.argtypes = [vp, C.c_int, C.c_int, vp]
     L.hsb_axpb_to_peers.argtypes = [vp, u32, u32, u32]
@@ -418,6 +419,10 @@ class Context:
     def iterate(self, iters, alpha_word, beta_word):
         """iters x { x <- alpha (*) A x (+) beta } on the device (PageRank-style power iteration)"""
         _check(lib().hsb_iterate(self.h, iters, int(alpha_word), int(beta_word)))
+
+    def iterate_peers(self, iters, alpha_word, beta_word, col_offset):
+        """hsb_iterate_peers: the multi-GPU iteration as one resident kernel per GPU (after peer_connect)"""
+        _check(lib().hsb_iterate_peers(self.h, iters, int(alpha_word), int(beta_word), int(col_offset)))
 
     def set_option(self, name, value):
         _check(lib().hsb_set_option(self.h, name.encode(), int(value)))

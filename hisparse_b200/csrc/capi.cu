@@ -1395,13 +1395,15 @@ int hsb_axpb_to_peers(hsb_ctx *c, uint32_t alpha_word, uint32_t beta_word, uint3
 namespace {
 // hsb_iterate as ONE cooperative launch (spmv_iterate_kernel): the grid stays resident and the two dependencies of an
 // iteration are grid-wide barriers instead of kernel boundaries. HSB_ITERATE_PERSISTENT=0: the launch-per-step form.
-int iterate_persistent(hsb_ctx *c, int iters, uint32_t alpha_word, uint32_t beta_word) {
+int iterate_persistent(hsb_ctx *c, int iters, uint32_t alpha_word, uint32_t beta_word, bool peers, uint32_t col_offset) {
     CUDA_TRY(cudaSetDevice(c->device));
     { int rc = finish(c); if (rc) return rc; }             // y final, every accumulator buffer zero, deferred download issued
     // the vector the first iteration reads has landed, and no upload is writing the buffer the iterations alternate with
     CUDA_TRY(cudaStreamSynchronize(c->s_h2d));
     CUDA_TRY(cudaStreamSynchronize(c->s_h2d_b));
     for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamSynchronize(c->s_h2d_more[i]));
+    // (multi-GPU: the current vector may still be arriving from the other ranks: the first iteration polls their flags)
+    const bool wait_first = peers && c->x_wait_buf == kXBuffers;
     c->x_wait_buf = -1; c->x_dirty = false;
     const int yb = c->y_cur;
     if (c->y_busy[yb]) {                                   // a download still reads y: order the rewrite behind it
@@ -1416,6 +1418,7 @@ int iterate_persistent(hsb_ctx *c, int iters, uint32_t alpha_word, uint32_t beta
     c->next_replica++;
     const uint32_t G = (uint32_t)c->sm_count;
     const int grid = (int)c->plan_grid[0];
+    const int iters_total = iters;
     while (iters > 0) {
         const int n = std::min(iters, 1 << 20);            // the barrier counter: 2 * grid per iteration, below 2^31
         const int b = (c->x_latest + 1) % nb;
@@ -1439,19 +1442,46 @@ int iterate_persistent(hsb_ctx *c, int iters, uint32_t alpha_word, uint32_t beta
         it.iters = (uint32_t)n; it.alpha = alpha_word; it.beta = beta_word;
         it.rows = c->rows; it.x_limit = c->x_words;
         CUDA_TRY(cudaMemsetAsync(it.barrier, 0, 4, c->stream));
-        CUDA_TRY(hsb::launch_iterate(c->arith, p, it, grid, c->smem_bytes, c->stream));
+        if (peers) {
+            // Every rank runs the same sequence, so buffer b is the same buffer everywhere; a rank can be at most one
+            // iteration ahead of the slowest one (it waits for everybody's slice), and four buffers rotate.
+            hsb::IteratePeers pr;
+            std::memset(&pr, 0, sizeof pr);
+            pr.world = (uint32_t)c->peer_world;
+            for (int g = 0; g < c->peer_world; g++) {
+                pr.x_base[g] = c->peer_x[g];
+                pr.flag[g] = c->peer_flags[g] + c->peer_rank;
+            }
+            pr.arrival = c->d_peer;
+            pr.x_stride = c->x_stride;
+            pr.buf0 = (uint32_t)c->x_latest; pr.seq0 = c->peer_seq; pr.col_offset = col_offset;
+            pr.wait_first = (wait_first && iters == iters_total) ? 1u : 0u;
+            it.x0 = c->d_x[0]; it.x1 = nullptr;
+            CUDA_TRY(hsb::launch_iterate(c->arith, p, it, &pr, grid, c->smem_bytes, c->stream));
+            c->peer_seq += (uint32_t)n;
+            for (int q = 0; q < kXBuffers; q++) c->x_reader_seq[q] = c->launch_seq;
+            c->x_latest = (c->x_latest + n) % kXBuffers;
+        } else {
+            CUDA_TRY(hsb::launch_iterate(c->arith, p, it, nullptr, grid, c->smem_bytes, c->stream));
+            // both buffers were read by this launch; its number appears in done_seq through the stream operation below
+            c->x_reader_seq[c->x_latest] = c->x_reader_seq[b] = c->launch_seq;
+            if (n & 1) c->x_latest = b;
+        }
         c->launches++;
-        // both buffers were read by this launch; its number appears in done_seq through the stream operation below
-        c->x_reader_seq[c->x_latest] = c->x_reader_seq[b] = c->launch_seq;
-        if (n & 1) c->x_latest = b;
         iters -= n;
     }
     (void)G;
     if (c->flags_mode) { int rc = publish_done(c); if (rc) return rc; }
     else CUDA_TRY(cudaEventRecord(c->ev_xfree[c->x_latest ^ 1], c->stream));
-    // the next SpMV is a programmatic launch that stages x before its griddepcontrol.wait: it has to wait for this grid first
-    c->x_after_grid = true;
     c->x_next_buf = -1;
+    c->x_next_from_peers = false;
+    if (peers) {
+        // the last slices of the other ranks may still be on their way: the next SpMV polls the arrival flags
+        c->x_wait_buf = kXBuffers; c->x_wait_val = c->peer_seq; c->x_wait_launch = 0;
+    } else {
+        // the next SpMV is a programmatic launch that stages x before its griddepcontrol.wait: it has to wait for this grid first
+        c->x_after_grid = true;
+    }
     return HSB_OK;
 }
 }  // namespace
@@ -1461,10 +1491,25 @@ int hsb_iterate(hsb_ctx *c, int iters, uint32_t alpha_word, uint32_t beta_word) 
     if (!c->have_matrix) return set_err(HSB_ESTATE, "upload a matrix first");
     if (c->rows > c->x_words) return set_err(HSB_EINVAL, "hsb_iterate needs rows <= columns (x <- f(A x))");
     // (a gather of y rides on the drains of the launch-per-step form; a pending update of the next vector belongs to it too)
-    if (c->iterate_persistent && iters > 0 && !c->d_gather && c->x_next_buf < 0) return iterate_persistent(c, iters, alpha_word, beta_word);
+    if (c->iterate_persistent && iters > 0 && !c->d_gather && c->x_next_buf < 0) return iterate_persistent(c, iters, alpha_word, beta_word, false, 0);
     for (int k = 0; k < iters; k++) {
         int rc = hsb_spmv(c);
         if (rc == HSB_OK) rc = hsb_axpb_to_vector(c, alpha_word, beta_word, 0);
+        if (rc == HSB_OK) rc = hsb_vector_commit(c);
+        if (rc) return rc;
+    }
+    return HSB_OK;
+}
+
+int hsb_iterate_peers(hsb_ctx *c, int iters, uint32_t alpha_word, uint32_t beta_word, uint32_t col_offset) {
+    if (!c || iters < 0) return set_err(HSB_EINVAL, "bad argument");
+    if (!c->have_matrix || c->peer_world < 1) return set_err(HSB_ESTATE, "call hsb_peer_connect first");
+    if (col_offset >= c->x_words) return set_err(HSB_EINVAL, "col_offset beyond the vector");
+    if (c->iterate_persistent && iters > 0 && !c->d_gather && c->x_next_buf < 0)
+        return iterate_persistent(c, iters, alpha_word, beta_word, true, col_offset);
+    for (int k = 0; k < iters; k++) {
+        int rc = hsb_spmv(c);
+        if (rc == HSB_OK) rc = hsb_axpb_to_peers(c, alpha_word, beta_word, col_offset);
         if (rc == HSB_OK) rc = hsb_vector_commit(c);
         if (rc) return rc;
     }

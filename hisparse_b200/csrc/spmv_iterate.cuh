@@ -55,8 +55,13 @@ __device__ __forceinline__ void drain_axpb_rows(void *acc, uint32_t *y, uint32_t
     }
 }
 
-template <class A, bool kNarrow>
-__global__ void __launch_bounds__(kThreads, 1) spmv_iterate_kernel(const SpmvParams p, const IterateParams it) {
+// kPeers: the matrix is a row-block shard and the vector lives on every GPU (hsb_peer_connect). The update stores this
+// rank's slice of the next vector into the x buffer of EVERY rank over NVLink; the CTA that arrives last at the second
+// barrier -- it knows every store of the grid has been issued and fenced -- raises this rank's arrival flag on every rank,
+// and the next iteration starts when the flags of ALL ranks (this one's included, which stands for the second barrier)
+// show the iteration's number: the whole multi-GPU iteration is one resident kernel per GPU, no host, no NCCL.
+template <class A, bool kNarrow, bool kPeers>
+__global__ void __launch_bounds__(kThreads, 1) spmv_iterate_kernel(const SpmvParams p, const IterateParams it, const IteratePeers pr) {
     unsigned char *smem_raw = reinterpret_cast<unsigned char *>(xs);
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t abort_flag, dead;
@@ -75,15 +80,20 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_iterate_kernel(const SpmvPar
     __syncthreads();
     uint32_t parity = 0;
     for (uint32_t k = 0; k < it.iters; k++) {
-        const uint32_t *x = (k & 1u) ? it.x1 : it.x0;
+        const uint32_t *x = kPeers ? it.x0 + (size_t)((pr.buf0 + k) & 3u) * pr.x_stride : ((k & 1u) ? it.x1 : it.x0);
         // The whole new vector, and every re-zeroed accumulator, before this iteration's first x tile is staged (the
         // row updates come after the tile). Only thread 0 waits: the other warps go ahead and fill their prefetch
         // rings with matrix data, which does not depend on x. A timed-out wait still stages the tile -- the warps
         // must be released -- but nobody multiplies (abort_flag), and the CTA leaves at the next barrier.
-        if (k > 0 && tid == 0 && !grid_wait(it.barrier, 2u * k * gridDim.x)) {
-            abort_flag = 1u;
-            dead = 1u;
-            raise_error(p.error_flag);
+        if (tid == 0 && (k > 0 || (kPeers && pr.wait_first))) {
+            bool ok = true;
+            if (kPeers) for (uint32_t g = 0; g < pr.world; g++) ok &= wait_flag_geq<kAcqSys>(pr.arrival + g, pr.seq0 + k);
+            else ok = grid_wait(it.barrier, 2u * k * gridDim.x);
+            if (!ok) {
+                abort_flag = 1u;
+                dead = 1u;
+                raise_error(p.error_flag);
+            }
         }
         for (uint32_t g = g0; g < g1; g++) {
             const Segment *sg = p.segs + g;
@@ -137,10 +147,33 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_iterate_kernel(const SpmvPar
         }
         __syncthreads();
         if (dead) break;
-        drain_axpb_rows<A>(p.acc, p.y, (k & 1u) ? it.x0 : it.x1, it.rows, it.x_limit, it.alpha, it.beta,
-                           blockIdx.x * kThreads + tid, gridDim.x * kThreads);
-        if (blockIdx.x == 0 && tid == 0) (void)A::drain(p.acc, p.trash_row);
-        if (k + 1u < it.iters) grid_arrive(it.barrier);            // waited for at the top of the next iteration
+        if (kPeers) {
+            const size_t wb = (size_t)((pr.buf0 + k + 1u) & 3u) * pr.x_stride + pr.col_offset;
+            for (uint32_t r = blockIdx.x * kThreads + tid; r < it.rows; r += gridDim.x * kThreads) {
+                const uint32_t v = A::drain(p.acc, r);
+                p.y[r] = v;
+                if (pr.col_offset + r < it.x_limit) {
+                    const uint32_t w = A::axpb(it.alpha, v, it.beta);
+                    for (uint32_t g = 0; g < pr.world; g++) pr.x_base[g][wb + r] = w;      // NVLink peer stores, coalesced
+                }
+            }
+            if (blockIdx.x == 0 && tid == 0) (void)A::drain(p.acc, p.trash_row);
+            // second barrier, arrive half, at system scope; the last CTA of the grid publishes the slice on every rank
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence_system();
+                if (atomicAdd(it.barrier, 1u) + 1u == (2u * k + 2u) * gridDim.x) {
+                    __threadfence_system();
+                    for (uint32_t g = 0; g < pr.world; g++)
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pr.flag[g]), "r"(pr.seq0 + k + 1u) : "memory");
+                }
+            }
+        } else {
+            drain_axpb_rows<A>(p.acc, p.y, (k & 1u) ? it.x0 : it.x1, it.rows, it.x_limit, it.alpha, it.beta,
+                               blockIdx.x * kThreads + tid, gridDim.x * kThreads);
+            if (blockIdx.x == 0 && tid == 0) (void)A::drain(p.acc, p.trash_row);
+            if (k + 1u < it.iters) grid_arrive(it.barrier);        // waited for at the top of the next iteration
+        }
     }
     // an ordinary launch: its predecessor was complete before it started
     if (blockIdx.x == 0 && tid == 0) {
@@ -152,8 +185,10 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_iterate_kernel(const SpmvPar
 }  // namespace
 
 cudaError_t configure_iterate_kernels() {
-    const void *kernels[] = {(const void *)spmv_iterate_kernel<FixedArith, false>, (const void *)spmv_iterate_kernel<FloatArith, false>,
-                             (const void *)spmv_iterate_kernel<FixedArith, true>, (const void *)spmv_iterate_kernel<FloatArith, true>};
+    const void *kernels[] = {(const void *)spmv_iterate_kernel<FixedArith, false, false>, (const void *)spmv_iterate_kernel<FloatArith, false, false>,
+                             (const void *)spmv_iterate_kernel<FixedArith, true, false>, (const void *)spmv_iterate_kernel<FloatArith, true, false>,
+                             (const void *)spmv_iterate_kernel<FixedArith, false, true>, (const void *)spmv_iterate_kernel<FloatArith, false, true>,
+                             (const void *)spmv_iterate_kernel<FixedArith, true, true>, (const void *)spmv_iterate_kernel<FloatArith, true, true>};
     for (const void *k : kernels) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) return e;
@@ -161,7 +196,8 @@ cudaError_t configure_iterate_kernels() {
     return cudaSuccess;
 }
 
-cudaError_t launch_iterate(int arith, const SpmvParams &p, const IterateParams &it, int grid, uint32_t smem_bytes, cudaStream_t stream) {
+cudaError_t launch_iterate(int arith, const SpmvParams &p, const IterateParams &it, const IteratePeers *peers, int grid,
+                           uint32_t smem_bytes, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
@@ -172,11 +208,14 @@ cudaError_t launch_iterate(int arith, const SpmvParams &p, const IterateParams &
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (p.narrow) {
-        if (arith == kArithFixed) return cudaLaunchKernelEx(&cfg, spmv_iterate_kernel<FixedArith, true>, p, it);
-        return cudaLaunchKernelEx(&cfg, spmv_iterate_kernel<FloatArith, true>, p, it);
-    }
-    if (arith == kArithFixed) return cudaLaunchKernelEx(&cfg, spmv_iterate_kernel<FixedArith, false>, p, it);
-    return cudaLaunchKernelEx(&cfg, spmv_iterate_kernel<FloatArith, false>, p, it);
+    IteratePeers none = {};
+    const IteratePeers &pr = peers ? *peers : none;
+    const bool fixed = arith == kArithFixed;
+#define HSB_ITER_LAUNCH(N, P)                                                                                   \
+    (fixed ? cudaLaunchKernelEx(&cfg, spmv_iterate_kernel<FixedArith, N, P>, p, it, pr)                         \
+           : cudaLaunchKernelEx(&cfg, spmv_iterate_kernel<FloatArith, N, P>, p, it, pr))
+    if (peers) return p.narrow ? HSB_ITER_LAUNCH(true, true) : HSB_ITER_LAUNCH(false, true);
+    return p.narrow ? HSB_ITER_LAUNCH(true, false) : HSB_ITER_LAUNCH(false, false);
+#undef HSB_ITER_LAUNCH
 }
 

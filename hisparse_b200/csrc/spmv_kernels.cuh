@@ -126,17 +126,9 @@ struct GatherTargets {
 enum { kArithFixed = 0, kArithFloat = 1 };
 
 cudaError_t launch_spmv(int arith, const SpmvParams &p, int grid, uint32_t smem_bytes, cudaStream_t stream);
-// `iters` iterations x <- alpha (*) (A x) (+) beta in one cooperative launch (spmv_iterate_kernel): iteration k reads
-// x0 (k even) / x1 (k odd) and writes the other; y holds A x of the last iteration; p.acc must be all zero and is left all zero.
-// grid <= number of SMs (one CTA per SM: every CTA resident). p: vals / cols / slice_rows / cta_seg / segs / acc / y /
-// trash_row / seq / done_dev / done_seq / error_flag / comb_offset / narrow as for launch_spmv, everything else zero.
-struct IterateParams {
-    uint32_t *x0, *x1;            // iteration k reads x0 (k even) or x1 (k odd) and writes the other
-    uint32_t *barrier;            // grid-barrier counter, zero at launch; iters * 2 * grid must stay below 2^31
-    uint32_t iters, alpha, beta;
-    uint32_t rows, x_limit;       // rows of the matrix; elements of x that may be written (x_next[r] for r < x_limit)
-};
-cudaError_t launch_iterate(int arith, const SpmvParams &p, const IterateParams &it, int grid, uint32_t smem_bytes, cudaStream_t stream);
+}  // namespace hsb
+#include "spmv_iterate.h"     // hsb_iterate as one cooperative launch: IterateParams, IteratePeers, launch_iterate
+namespace hsb {
 // drain only: y[r] = clamp(acc[r]), acc[r] = 0 for r in [row_begin, row_end) and the trash slot; y_host (device alias of a
 // mapped page-locked host buffer, or null): rows < y_host_rows are ALSO written there (a download without the copy engine)
 cudaError_t launch_drain(int arith, void *acc, uint32_t *y, uint32_t row_begin, uint32_t row_end,

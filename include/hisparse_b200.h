@@ -165,6 +165,13 @@ int hsb_vector_commit(hsb_ctx *ctx);
 int hsb_peer_export(hsb_ctx *ctx, void *blob);
 int hsb_peer_connect(hsb_ctx *ctx, int world, int rank, const void *blobs /* world x HSB_PEER_BLOB_BYTES */);
 int hsb_axpb_to_peers(hsb_ctx *ctx, uint32_t alpha_word, uint32_t beta_word, uint32_t col_offset);
+/* iters x { hsb_spmv; hsb_axpb_to_peers(alpha, beta, col_offset); hsb_vector_commit } as ONE resident kernel per GPU
+ * (a cooperative launch, as hsb_iterate): the SpMV and the update are separated by a grid barrier, the iterations by the
+ * arrival flags of all ranks -- the multi-GPU iteration is a single kernel, no host and no NCCL inside. Every rank calls
+ * it with the same iters; afterwards y = this rank's rows of A x of the last iteration and the current vector is the
+ * updated one on every rank (the next SpMV polls the last arrival flags). Needs all of the device's SMs for one grid:
+ * ranks that share a GPU cannot be resident together (use the launch-per-step calls there). */
+int hsb_iterate_peers(hsb_ctx *ctx, int iters, uint32_t alpha_word, uint32_t beta_word, uint32_t col_offset);
 /* Gather of y across row-block shards, fused into the result drain (the role of axis_merge +
  * spmv_result_drain, spmv/libfpga/stream_utils.h:36-75 and spmv/spmv_result_drain.cpp:36-113, which assemble
  * ONE y from the 16 clusters' streams): once connected, every drain of this context ALSO stores its result

@@ -78,6 +78,10 @@ def main():
     def iterate(n):
         if p2p:
             # compute + all-gather in one kernel, arrival flags polled by the next SpMV: the host only enqueues
+            if not args.step_form:
+                ctx.iterate_peers(n, alpha, beta, bounds[rank])      # the whole iteration loop: one resident kernel per GPU
+                ctx.sync()
+                return
             for _ in range(n):
                 ctx.spmv()
                 ctx.axpb_to_peers(alpha, beta, bounds[rank])
@@ -112,7 +116,7 @@ def main():
     y = ctx.download_result()
     out = {"nodes": r2, "nnz": int(ip2[-1]), "impl": args.impl, "n_gpus": world, "iters": args.iters,
            "ms_per_iteration": 1e3 * sec, "gops": 2.0 * int(ip2[-1]) / sec / 1e9,
-           "exchange": "peer-memory stores + arrival flags inside the update kernel" if p2p else
+           "exchange": ("peer-memory stores + arrival flags inside " + ("the update kernel" if args.step_form else "one resident kernel per GPU")) if p2p else
                        ("NCCL broadcasts issued by the host" if world > 1 else ("none (single GPU, launch per step)" if args.step_form else "none (single GPU, one cooperative launch)")),
            "what": "spmv + fused drain/axpb + exchange of the x blocks + commit, per iteration"}
     if args.check:

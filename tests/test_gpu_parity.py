@@ -1210,3 +1210,89 @@ def test_two_contexts_iterate_concurrently(gpu, port):
     for t in th: t.join()
     for c in ctxs: c.close()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("narrow", [0, 1], ids=["wide", "narrow"])
+def test_iterate_peers_one_kernel_single_rank(gpu, port, monkeypatch, narrow):
+    """hsb_iterate_peers with a world of one: the resident kernel stores its slice through the peer table, raises its own
+    arrival flag from the last CTA of the second barrier and starts the next iteration on that flag; mixed with the
+    launch-per-step calls (the arrival sequence numbers continue), bit-exact"""
+    monkeypatch.setenv("HSB_NARROW", str(narrow))
+    r2, c2, ip2, indices, data = _pagerank_matrix(6000, 90000, 73)
+    words = port.quantize(data)
+    alpha, beta = int(port.quantize(np.float32([0.85]))[0]), int(port.quantize(np.float32([0.02]))[0])
+    x0 = port.quantize(np.full(c2, 0.125, np.float32))
+    ctx = capi.Context(0, capi.IMPL_FIXED)
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+    ctx.upload_vector(x0)
+    ctx.peer_connect(1, 0, ctx.peer_export())
+    x = x0.copy()
+
+    def advance(n):
+        nonlocal x
+        for _ in range(n):
+            y = port.spmv_q824(ip2, indices, words, x)
+            x = hsoracle.axpb_q824(alpha, y, beta)
+        return y
+
+    ctx.iterate_peers(5, alpha, beta, 0)
+    assert np.array_equal(ctx.download_result(), advance(5))
+    for _ in range(2):                                    # launch-per-step form in between
+        ctx.spmv(); ctx.axpb_to_peers(alpha, beta, 0); ctx.vector_commit()
+    advance(2)
+    ctx.iterate_peers(4, alpha, beta, 0)                  # starts on a vector announced by arrival flags (wait_first)
+    assert np.array_equal(ctx.download_result(), advance(4))
+    ctx.spmv()
+    assert np.array_equal(ctx.download_result(), port.spmv_q824(ip2, indices, words, x))
+    ctx.close()
+
+
+def test_iterate_peers_one_kernel_two_gpus(gpu, port):
+    """two GPUs, one host thread and one context each, the matrix split into two row blocks: every iteration of the
+    resident kernels exchanges the slices over NVLink (peer stores + arrival flags). Skipped on a one-GPU box."""
+    import threading
+    from hisparse_b200 import sharding
+    if capi.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    r2, c2, ip2, indices, data = _pagerank_matrix(40000, 1200000, 79)
+    words = port.quantize(data)
+    alpha, beta = int(port.quantize(np.float32([0.85]))[0]), int(port.quantize(np.float32([0.02]))[0])
+    x0 = port.quantize(np.full(c2, 0.125, np.float32))
+    iters = 40
+    x = x0.copy()
+    for _ in range(iters):
+        y = port.spmv_q824(ip2, indices, words, x)
+        x = hsoracle.axpb_q824(alpha, y, beta)
+    want_next = port.spmv_q824(ip2, indices, words, x)
+    bounds = sharding.shard_bounds(ip2, 2)
+    ctxs = []
+    for g in range(2):
+        sip, six, sw = sharding.extract_shard(ip2, indices, words, bounds[g], bounds[g + 1])
+        c = capi.Context(g, capi.IMPL_FIXED)
+        c.upload_matrix_csr(bounds[g + 1] - bounds[g], c2, sip, six, sw)
+        c.upload_vector(x0)
+        c.sync()
+        ctxs.append(c)
+    blobs = np.concatenate([c.peer_export() for c in ctxs])
+    for g, c in enumerate(ctxs):
+        c.peer_connect(2, g, blobs)
+    errors = []
+
+    def drive(g):
+        try:
+            c = ctxs[g]
+            c.iterate_peers(iters // 2, alpha, beta, bounds[g])
+            c.iterate_peers(iters - iters // 2, alpha, beta, bounds[g])
+            if not np.array_equal(c.download_result(), y[bounds[g]:bounds[g + 1]]):
+                errors.append((g, "y of the last iteration"))
+            c.spmv()
+            if not np.array_equal(c.download_result(), want_next[bounds[g]:bounds[g + 1]]):
+                errors.append((g, "SpMV on the iterated vector"))
+        except Exception as e:                      # noqa: BLE001
+            errors.append((g, repr(e)))
+
+    th = [threading.Thread(target=drive, args=(g,)) for g in range(2)]
+    for t in th: t.start()
+    for t in th: t.join()
+    for c in ctxs: c.close()
+    assert not errors, errors
