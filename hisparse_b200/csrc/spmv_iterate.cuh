@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_iterate_kernel(const SpmvPar
                 if (atomicAdd(it.barrier, 1u) + 1u == (2u * k + 2u) * gridDim.x) {
                     __threadfence_system();
                     for (uint32_t g = 0; g < pr.world; g++)
-                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pr.flag[g]), "r"(pr.seq0 + k + 1u) : "memory");
+                        publish_flag(pr.flag[g], pr.seq0 + k + 1u);
                 }
             }
         } else {

@@ -143,6 +143,19 @@ __device__ __forceinline__ bool wait_flag_geq(const uint32_t *flag, uint32_t val
 __device__ __forceinline__ bool wait_flag_geq(const uint32_t *flag, uint32_t val, bool acquire) {
     return acquire ? wait_flag_geq<kAcqSys>(flag, val) : wait_flag_geq<kAcqNone>(flag, val);
 }
+// An arrival flag on a peer GPU (or this one), written AFTER a system-scope fence that ordered the data stores: fence +
+// relaxed store is a release pattern. (`st.release.sys` per target instead makes every store wait for the previous one's
+// NVLink round trip: the publication then costs one round trip per rank -- HSB_FLAG_RELEASE_STORES=1 builds that form.)
+#ifndef HSB_FLAG_RELEASE_STORES
+#define HSB_FLAG_RELEASE_STORES 0
+#endif
+__device__ __forceinline__ void publish_flag(uint32_t *flag, uint32_t seq) {
+#if HSB_FLAG_RELEASE_STORES
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+#else
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+#endif
+}
 // Grid-wide completion of a drain with a gather epilogue: the CTA that takes the last ticket knows every
 // peer store of this drain has been issued and fenced, and raises this rank's arrival flag on every target.
 __device__ __forceinline__ void gather_publish(const GatherTargets *gt, uint32_t seq) {
@@ -153,7 +166,7 @@ __device__ __forceinline__ void gather_publish(const GatherTargets *gt, uint32_t
             *gt->ticket = 0u;
             __threadfence_system();
             for (int g = 0; g < gt->n; g++)
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(gt->flag[g]), "r"(seq) : "memory");
+                publish_flag(gt->flag[g], seq);
         }
     }
 }
@@ -790,7 +803,7 @@ __global__ void axpb_peers_kernel(void *acc, uint32_t *y, const PeerTargets t, u
             *ticket = 0u;
             __threadfence_system();
             for (int g = 0; g < t.world; g++)
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.flag[g]), "r"(seq) : "memory");
+                publish_flag(t.flag[g], seq);
         }
     }
 }
