@@ -1420,7 +1420,10 @@ int iterate_persistent(hsb_ctx *c, int iters, uint32_t alpha_word, uint32_t beta
     const int grid = (int)c->plan_grid[0];
     const int iters_total = iters;
     while (iters > 0) {
-        const int n = std::min(iters, 1 << 20);            // the barrier counter: 2 * grid per iteration, below 2^31
+        // iterations per launch: the barrier counter takes 2 * grid per iteration and stays below 2^31 (HSB_ITERATE_CHUNK:
+        // a small value for the tests of the hand-over between two launches)
+        static const int chunk = [] { const char *v = std::getenv("HSB_ITERATE_CHUNK"); return v && std::atoi(v) > 0 ? std::atoi(v) : (1 << 20); }();
+        const int n = std::min(iters, chunk);
         const int b = (c->x_latest + 1) % nb;
         hsb::SpmvParams p;
         std::memset(&p, 0, sizeof p);
@@ -1455,7 +1458,8 @@ int iterate_persistent(hsb_ctx *c, int iters, uint32_t alpha_word, uint32_t beta
             pr.arrival = c->d_peer;
             pr.x_stride = c->x_stride;
             pr.buf0 = (uint32_t)c->x_latest; pr.seq0 = c->peer_seq; pr.col_offset = col_offset;
-            pr.wait_first = (wait_first && iters == iters_total) ? 1u : 0u;
+            // (a later chunk of a very long run starts on slices the other ranks stored at the end of the previous one)
+            pr.wait_first = (wait_first || iters != iters_total) ? 1u : 0u;
             it.x0 = c->d_x[0]; it.x1 = nullptr;
             CUDA_TRY(hsb::launch_iterate(c->arith, p, it, &pr, grid, c->smem_bytes, c->stream));
             c->peer_seq += (uint32_t)n;

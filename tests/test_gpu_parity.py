@@ -1296,3 +1296,47 @@ def test_iterate_peers_one_kernel_two_gpus(gpu, port):
     for t in th: t.join()
     for c in ctxs: c.close()
     assert not errors, errors
+
+
+def test_iterate_split_over_several_launches(gpu):
+    """a long run is cut into several cooperative launches (HSB_ITERATE_CHUNK=3 here, 2^20 iterations normally): the
+    vector, the buffer rotation and -- with peers -- the arrival sequence numbers carry over from one launch to the next.
+    (A subprocess: the chunk size is read once per process.)"""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, sys
+sys.path.insert(0, %r)
+from hisparse_b200 import capi, matgen
+from oracle import hsoracle
+port = hsoracle.Port()
+rows, cols, indptr, indices, _ = matgen.rmat_csr(3000, 50000, 83)
+outdeg = np.maximum(np.bincount(indices, minlength=cols), 1)
+data = (1.0 / outdeg[indices]).astype(np.float32)
+r2, c2, ip2 = matgen.pad_csr(rows, cols, indptr, 128, 128)
+words = port.quantize(data)
+alpha, beta = int(port.quantize(np.float32([0.85]))[0]), int(port.quantize(np.float32([0.02]))[0])
+x0 = port.quantize(np.full(c2, 0.125, np.float32))
+x = x0.copy()
+for _ in range(10):
+    y = port.spmv_q824(ip2, indices, words, x)
+    x = hsoracle.axpb_q824(alpha, y, beta)
+for peers in (False, True):
+    ctx = capi.Context(0, "fixed")
+    ctx.upload_matrix_csr(r2, c2, ip2, indices, words)
+    ctx.upload_vector(x0)
+    if peers:
+        ctx.peer_connect(1, 0, ctx.peer_export())
+        ctx.iterate_peers(10, alpha, beta, 0)
+    else:
+        ctx.iterate(10, alpha, beta)
+    assert np.array_equal(ctx.download_result(), y), peers
+    ctx.spmv()
+    assert np.array_equal(ctx.download_result(), port.spmv_q824(ip2, indices, words, x)), peers
+    assert ctx.stats()["kernel_launches"] >= 4
+    ctx.close()
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HSB_ITERATE_CHUNK="3")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
