@@ -648,6 +648,10 @@ hsb_ctx *hsb_create(int device, int impl) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_h2d_b, cudaStreamNonBlocking);
     for (int i = 0; i < 2; i++) if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_h2d_more[i], cudaStreamNonBlocking);
     if (const char *v = std::getenv("HSB_ITERATE_PERSISTENT")) c->iterate_persistent = std::atoi(v) != 0;
+    {   // the one-launch iteration needs cooperative launches (every CTA of the grid resident)
+        int coop = 0;
+        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop) { cudaGetLastError(); c->iterate_persistent = false; }
+    }
     if (const char *v = std::getenv("HSB_UPLOAD_STREAMS")) c->n_upload_streams = std::min(4, std::max(1, std::atoi(v)));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
     cudaEvent_t *evs[] = {&c->ev_xready, &c->ev_xfree[0], &c->ev_xfree[1], &c->ev_yready, &c->ev_ydone};
