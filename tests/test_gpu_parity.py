@@ -1097,7 +1097,7 @@ def test_two_host_threads_two_contexts(gpu, port):
 
 
 @pytest.mark.parametrize("narrow", [0, 1], ids=["wide", "narrow"])
-@pytest.mark.parametrize("n,nnz", [(600, 9000), (6000, 90000), (60000, 1500000)])
+@pytest.mark.parametrize("n,nnz", [(600, 9000), (6000, 90000), (60000, 1500000), (200000, 2400000)])   # the last one: several rows per thread in the update (128-bit path)
 def test_iterate_one_launch_against_oracle_and_step_form(gpu, port, monkeypatch, narrow, n, nnz):
     """hsb_iterate as ONE cooperative launch (grid barriers between the SpMV and the update of x): the vector after k
     iterations, y of the last iteration and the following SpMV are bit-equal to the oracle's iteration and to the
