@@ -26,7 +26,7 @@ for line in out.splitlines():
         for mm in pat.findall(body):
             counts[fn][mm] += 1
 for fn, c in counts.items():
-    if not any(k in fn for k in ("spmv_tiles_kernel", "drain_kernel", "axpb", "wait_flags", "k_decode", "k_fill")):
+    if not any(k in fn for k in ("spmv_tiles_kernel", "spmv_iterate_kernel", "drain_kernel", "axpb", "wait_flags", "k_decode", "k_fill")):
         continue
     print(fn[:150])
     print("   " + "  ".join("%s x%d" % kv for kv in sorted(c.items(), key=lambda kv: (-kv[1], kv[0]))))
