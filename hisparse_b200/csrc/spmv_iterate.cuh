@@ -13,10 +13,30 @@ namespace {
 // Grid barrier in two halves on a monotonic counter: every CTA arrives once per barrier (after a CTA-wide barrier: thread
 // 0's fence is cumulative over what the other threads wrote), and barrier number b (1, 2, ...) is complete when the
 // counter has reached b * gridDim.x. A CTA waits for barrier b before it arrives at b + 1, so the count cannot run ahead.
+// The barriers' fences: __threadfence[_system]() emit the sequentially consistent form (MEMBAR.SC). Acquire-release is all
+// the release / acquire patterns need (HSB_ITER_SC_FENCES=0 builds that form), but it measures the same on one and on
+// two GPUs (tools/iterate_fence_ab.sh: 5.12 / 5.11, 19.95 / 19.98, 10.25 / 10.28, 18.66 / 18.71 us), so the stronger one stays.
+#ifndef HSB_ITER_SC_FENCES
+#define HSB_ITER_SC_FENCES 1
+#endif
+__device__ __forceinline__ void fence_gpu() {
+#if HSB_ITER_SC_FENCES
+    __threadfence();
+#else
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void fence_sys() {
+#if HSB_ITER_SC_FENCES
+    __threadfence_system();
+#else
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void grid_arrive(uint32_t *word) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        fence_gpu();
         atomicAdd(word, 1u);
     }
 }
@@ -161,9 +181,9 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_iterate_kernel(const SpmvPar
             // second barrier, arrive half, at system scope; the last CTA of the grid publishes the slice on every rank
             __syncthreads();
             if (tid == 0) {
-                __threadfence_system();
+                fence_sys();
                 if (atomicAdd(it.barrier, 1u) + 1u == (2u * k + 2u) * gridDim.x) {
-                    __threadfence_system();
+                    fence_sys();
                     for (uint32_t g = 0; g < pr.world; g++)
                         publish_flag(pr.flag[g], pr.seq0 + k + 1u);
                 }
