@@ -327,3 +327,15 @@ def test_binding_refuses_float64_words():
         capi._words(np.array([1 << 33], np.int64))
     a = np.array([0.5], np.float32)
     assert capi._words(a).view(np.float32)[0] == np.float32(0.5)
+
+
+def test_traffic_evidence_is_keyed_to_the_current_kernel_sources():
+    """profiles/traffic.json (the ncu DRAM bytes bench.py quotes as roofline.traffic) carries the hash of the kernel and
+    format sources it was captured on; bench.py drops the figure when the hash differs. This keeps the committed
+    evidence and the committed sources in step: after a kernel edit, re-run tools/final_capture.sh."""
+    import json
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    t = json.load(open(os.path.join(here, "profiles", "traffic.json")))
+    assert t["source_sha256"] == capi.source_hash()
+    assert t["dram_bytes_per_launch"] == t["dram_read"] + t["dram_write"]
